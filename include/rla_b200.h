@@ -1,0 +1,188 @@
+/* rla_b200.h -- C ABI of librla_b200.so, the B200 (sm_100a) sketching engine
+ * behind rla4mor's embedding-operator API.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success or a negative rla_status code;
+ *     rla_last_error() returns a thread-local message for the last failure;
+ *   - a block of m vectors of dimension n is an (m, n) array, ONE VECTOR PER
+ *     ROW with n contiguous (the reference's layout: rla/srht.py:142,160 and
+ *     `U.to_numpy()` at rla/embeddings.py:169); `ld*` arguments are row
+ *     strides in ELEMENTS;
+ *   - pointers named *_dev are device pointers owned by the caller (PyTorch
+ *     tensors on the host side); nothing here allocates device memory: sizes
+ *     of plans and workspaces are queried and the caller provides the buffers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all device work is enqueued on it and the call returns without syncing;
+ *   - there is no CPU fallback: every compute entry point fails with
+ *     RLA_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Each entry point cites the reference interface it replaces (file:line into
+ * alexandre-pasco/rla4mor).  INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef RLA_B200_H
+#define RLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rla_status {
+    RLA_OK = 0,
+    RLA_ERR_INVALID = -1,   /* bad argument (the reference's AssertionError cases) */
+    RLA_ERR_CUDA = -2,      /* CUDA runtime / launch failure, or no device */
+    RLA_ERR_WORKSPACE = -3, /* workspace too small */
+    RLA_ERR_UNSUPPORTED = -4
+} rla_status;
+
+int rla_version(void);
+const char *rla_last_error(void);
+
+/* ------------------------------------------------------------------ SRHT ---
+ * Replaces srht(x, k, seed, nthreads)            rla/srht.py:136-177
+ * as called by SrhtEmbedding.apply               rla/embeddings.py:167-172.
+ *
+ * The Rademacher signs and the k row indices are drawn ON THE HOST by NumPy's
+ * legacy RandomState exactly as rla/srht.py:162-163 does (that is what makes
+ * them bit-exact) and handed to rla_srht_plan_create, which turns them into
+ * the device-side descriptor the kernel consumes (packed sign bits per tile,
+ * de-duplicated / bank-sorted sample descriptors, slot map).  The plan is
+ * host-only; rla_srht_plan_upload copies its device image into a caller-owned
+ * buffer of rla_srht_plan_device_bytes bytes.
+ */
+typedef struct rla_srht_plan rla_srht_plan;
+
+int rla_srht_plan_create(rla_srht_plan **plan,
+                         const int8_t *signs_host,  /* n entries, +1 / -1   (srht.py:162) */
+                         int64_t n,
+                         const int64_t *idx_host,   /* k entries in [0, 2**ceil(log2 n))  (srht.py:163) */
+                         int64_t k,
+                         int elem_bytes);           /* 8 (f64) or 4 (f32): the shared-memory layout depends on it */
+void rla_srht_plan_destroy(rla_srht_plan *plan);
+size_t rla_srht_plan_device_bytes(const rla_srht_plan *plan);
+int rla_srht_plan_upload(rla_srht_plan *plan, void *plan_dev, void *stream);
+/* number of passes over x the plan needs (1 unless k has more than 4096 distinct indices) */
+int rla_srht_plan_passes(const rla_srht_plan *plan);
+/* bytes of scratch needed to sketch m vectors with this plan */
+size_t rla_srht_workspace_bytes(const rla_srht_plan *plan, int64_t m);
+
+/* y[c, i] = scale * sum_j (-1)^popcount(idx[i] & j) * signs[j] * x[c, j]
+ * (scale = 1/sqrt(k) reproduces srht.py:165-171).
+ * x is read exactly once per pass and never written (srht.py:156). */
+int rla_srht_apply_f64(const rla_srht_plan *plan, const double *x_dev, int64_t m, int64_t ldx,
+                       double scale, double *y_dev, int64_t ldy,
+                       void *ws_dev, size_t ws_bytes, void *stream);
+int rla_srht_apply_f32(const rla_srht_plan *plan, const float *x_dev, int64_t m, int64_t ldx,
+                       float scale, float *y_dev, int64_t ldy,
+                       void *ws_dev, size_t ws_bytes, void *stream);
+
+/* Explicit rows of the SRHT matrix.  Replaces SrhtEmbedding._get_random_rows,
+ * rla/embeddings.py:195-209:
+ *   out[i, j] = value * (-1)^popcount(idx[rows[i]] & j) * signs[j],  j < n
+ * `value` is computed by the caller as fl(fl(sqrt(n/k)) * fl(1/2**(d/2))) so the
+ * result is bit-identical to the reference's. */
+int rla_srht_rows_f64(const int8_t *signs_dev, int64_t n, const int64_t *idx_dev,
+                      const int64_t *rows_dev, int64_t nrows, double value,
+                      double *out_dev, int64_t ldo, void *stream);
+
+/* ------------------------------------------------------------------ FWHT ---
+ * Replaces fht_oop(a, nthreads) / fht_ip(a)      rla/srht.py:121-134, 99-118.
+ * out = post_scale * H a along each row (H the natural-order Sylvester matrix,
+ * n_pow2 = 2**d); out_dev may equal a_dev (in place).  The reference's
+ * normalisation is post_scale = 1/2**(d/2) (srht.py:36). */
+int rla_fwht_f64(const double *a_dev, int64_t m, int64_t n_pow2, int64_t lda,
+                 double *out_dev, int64_t ldo, double post_scale, void *stream);
+int rla_fwht_f32(const float *a_dev, int64_t m, int64_t n_pow2, int64_t lda,
+                 float *out_dev, int64_t ldo, float post_scale, void *stream);
+
+/* Adjoint of the SRHT rows matrix without materialising it
+ * (replaces the dense GEMM of SrhtEmbedding.apply_adjoint, rla/embeddings.py:175-178):
+ *   out[c, j] = value * signs[j] * sum_i (-1)^popcount(idx[i] & j) * v[c, i],  j < n
+ * scratch: m * 2**d elements (rla_srht_adjoint_workspace_bytes). */
+size_t rla_srht_adjoint_workspace_bytes(int64_t m, int64_t n);
+int rla_srht_adjoint_f64(const int8_t *signs_dev, int64_t n, const int64_t *idx_dev, int64_t k,
+                         const double *v_dev, int64_t m, int64_t ldv, double value,
+                         double *out_dev, int64_t ldo, void *ws_dev, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------- dense embeddings ------
+ * Y(m, k) = U(m, n) * Theta(k, n)^T, both operands n-contiguous.
+ * Replaces NumpyMatrixOperator(Theta).apply(Q U) = (Theta @ (QU)^T)^T
+ *   GaussianEmbedding.apply                      rla/embeddings.py:250-254
+ *   BlockGaussianEmbedding.apply (per block)     rla/embeddings.py:425-434
+ * FP64 tensor-core (DMMA) GEMM with a deterministic split of the n dimension.
+ */
+size_t rla_gemm_workspace_bytes(int64_t m, int64_t k, int64_t n);
+
+/* Theta materialised in device memory (drawn by the host exactly as
+ * rla/embeddings.py:265-270 does). */
+int rla_gauss_apply_explicit_f64(const double *theta_dev, int64_t k, int64_t n, int64_t ldt,
+                                 const double *u_dev, int64_t m, int64_t ldu,
+                                 double *y_dev, int64_t ldy,
+                                 void *ws_dev, size_t ws_bytes, void *stream);
+
+/* Theta generated on the fly from a counter-based RNG (Philox4x32-10 keyed by
+ * `seed`), never materialised: element (row0 + i, col0 + j) of the virtual
+ * k_total x n_total matrix is scale * g(seed, row0 + i, col0 + j) with g a
+ * standard normal (kind 0, Box-Muller) or a Rademacher +-1 (kind 1).
+ * y[c, i] (+)= sum_j theta[row0 + i, col0 + j] * u[c, j]   for i < k_blk, j < n. */
+int rla_embed_apply_rng_f64(uint64_t seed, int kind, double scale,
+                            int64_t row0, int64_t k_blk, int64_t col0, int64_t n,
+                            const double *u_dev, int64_t m, int64_t ldu,
+                            double *y_dev, int64_t ldy, int accumulate,
+                            void *ws_dev, size_t ws_bytes, void *stream);
+int rla_embed_apply_rng_f32(uint64_t seed, int kind, float scale,
+                            int64_t row0, int64_t k_blk, int64_t col0, int64_t n,
+                            const float *u_dev, int64_t m, int64_t ldu,
+                            float *y_dev, int64_t ldy, int accumulate,
+                            void *ws_dev, size_t ws_bytes, void *stream);
+
+/* Export what the on-the-fly generator produces (parity tooling; replaces
+ * get_random_matrix / _get_random_block, rla/embeddings.py:87-100, 452-461). */
+int rla_theta_materialize_f64(uint64_t seed, int kind, double scale,
+                              int64_t row0, int64_t rows, int64_t col0, int64_t cols,
+                              double *out_dev, int64_t ldo, void *stream);
+
+/* out(m, n) = V(m, k) * Theta(k, n): the adjoint / explicit-matrix product
+ * (SrhtEmbedding.apply_adjoint rla/embeddings.py:175-178, rb.lincomb(T.T)
+ * mor/sketched_reductor.py:99-100). */
+int rla_gemm_nn_f64(const double *v_dev, int64_t m, int64_t k, int64_t ldv,
+                    const double *theta_dev, int64_t n, int64_t ldt,
+                    double *out_dev, int64_t ldo, void *stream);
+
+/* ------------------------------------------------ sketched reductor ops ----
+ * CSR SpMM in the reference's row layout: out[c, i] = sum_j A[i, j] * u[c, j]
+ * (the A_q.apply(U) that precedes every sketch, mor/sketched_reductor.py:69-70). */
+int rla_spmm_csr_f64(const int64_t *rowptr_dev, const int32_t *col_dev, const double *val_dev,
+                     int64_t n_rows, int64_t n_cols,
+                     const double *u_dev, int64_t m, int64_t ldu,
+                     double *out_dev, int64_t ldo, void *stream);
+
+/* Modified Gram-Schmidt with re-iteration of the r rows (dimension k) of the
+ * sketched basis, in place; R (r x r, row-major, ld = r) receives the
+ * coefficients as pyMOR's gram_schmidt(..., return_R=True) does
+ * (mor/sketched_reductor.py:94).  Rows [0, offset) are assumed orthonormal.
+ * flags_dev[i] = 1 when row i was dropped as (numerically) dependent. */
+int rla_gram_schmidt_f64(double *a_dev, int64_t r, int64_t k, int64_t lda, int64_t offset,
+                         double *R_dev, int32_t *flags_dev,
+                         double atol, double rtol, double reiteration_threshold, void *stream);
+
+/* Singular values / one-sided Jacobi SVD of a small k x m sketch (m <= k):
+ * A (k, m) row-major is overwritten by U * diag(s); s_dev gets the m singular
+ * values (unsorted); V_dev (m x m, may be NULL) the right vectors. */
+int rla_svd_jacobi_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
+                       double *s_dev, double *V_dev, int max_sweeps, void *stream);
+
+/* Sketched residual norm  || sum_q th[q] S_q a - sum_p tr[p] b_p ||_2
+ * (ResidualErrorEstimator.estimate_error, mor/sketched_reductor.py:216-219);
+ * S_dev is Q contiguous k x r row-major blocks, b_dev P contiguous k-vectors. */
+int rla_residual_norm_f64(const double *S_dev, int64_t Q, int64_t k, int64_t r,
+                          const double *th_dev, const double *a_dev,
+                          const double *b_dev, int64_t P, const double *tr_dev,
+                          double *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLA_B200_H */

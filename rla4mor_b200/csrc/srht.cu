@@ -1,0 +1,465 @@
+// srht.cu -- fused SRHT: sign flip -> Walsh-Hadamard -> row subsample, one pass over HBM.
+//
+// Replaces srht(x, k, seed) (rla/srht.py:136-177) as called by
+// SrhtEmbedding.apply (rla/embeddings.py:167-172).
+//
+// Math:  y[c,i] = scale * sum_j (-1)^popcount(s_i & j) r_j x[c,j].
+// Split j = jh*4096 + jl and s_i = sh_i*4096 + sl_i (H_{2^d} = H_{2^a} (x) H_{4096}):
+//     y[c,i] = scale * sum_jh (-1)^popcount(sh_i & jh) * T_jh[sl_i],
+//     T_jh   = H_4096 (r .* x[c, jh*4096 : (jh+1)*4096])
+// so only a 12-stage transform is done per 4096-element tile (in registers, one
+// swizzled shared-memory transpose in the middle); the remaining d-12 stages
+// collapse, for the k sampled outputs only, into one signed gather-accumulate per
+// (sample, tile).  x is read from HBM exactly once and never written.
+//
+// Work decomposition: CTA = 128 threads = two 64-thread groups, one tile per
+// group per iteration; each CTA owns a power-of-two chunk of consecutive tiles
+// of ONE vector (row of x) and keeps NSLOT sample accumulators per thread in
+// registers.  Tiles are visited in Gray-code order so the per-sample sign
+// (-1)^popcount(sh & jh) is maintained by one conditional sign flip of the
+// accumulator per step (integer XOR, no popcount, no FP64 op).  Per-chunk partial
+// sketches go to a workspace and are summed in chunk order by a small finalize
+// kernel (deterministic, no atomics).
+#include "common.cuh"
+#include <algorithm>
+#include <new>
+#include <vector>
+#include <stdlib.h>
+#include <string.h>
+
+namespace rla {
+
+constexpr int TILE_LOG2 = 12;
+constexpr int TILE = 1 << TILE_LOG2;     // elements per tile
+constexpr int GROUP = 64;                // threads per tile
+constexpr int CTA = 128;                 // two tiles per iteration
+constexpr int MAX_NSLOT = 32;            // sample accumulators per thread
+constexpr int MAX_SLOTS = MAX_NSLOT * CTA;
+
+// Position of tile element e in the shared-memory tile buffer.  The tile is a
+// 64 x 64 matrix (A = bits 1..6 of e, B = bit 0 and bits 7..11); round 1 holds one
+// A per thread, round 2 one B per thread; XOR swizzle keeps both sides bank-conflict
+// free (mask 15 for 8-byte words: 16 lanes per wavefront; 31 for 4-byte words).
+__host__ __device__ __forceinline__ int tile_pos(int e, int mask) {
+    int A = (e >> 1) & 63;
+    int B = (e & 1) | ((e >> 7) << 1);
+    return B * 64 + (A ^ (B & mask));
+}
+
+template <typename T> struct Elem;
+template <> struct Elem<double> {
+    static constexpr int MASK = 15;
+    __device__ static __forceinline__ void load2(const double *p, double &a, double &b) {
+        double2 v = ldg_stream_f64x2(p); a = v.x; b = v.y;
+    }
+    __device__ static __forceinline__ double load1(const double *p) { return ldg_stream_f64(p); }
+};
+template <> struct Elem<float> {
+    static constexpr int MASK = 31;
+    __device__ static __forceinline__ void load2(const float *p, float &a, float &b) {
+        float2 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+        a = v.x; b = v.y;
+    }
+    __device__ static __forceinline__ float load1(const float *p) { return ldg_stream_f32(p); }
+};
+
+// 6 radix-2 stages over the 64 registers of one thread
+template <typename T>
+__device__ __forceinline__ void butterflies64(T (&v)[64]) {
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            if ((i & (1 << b)) == 0) {
+                T p = v[i], q = v[i | (1 << b)];
+                v[i] = p + q;
+                v[i | (1 << b)] = p - q;
+            }
+        }
+    }
+}
+
+// Sign-flipped load of one tile into the round-1 register layout:
+// register rho = 2*h + l  <->  tile element e = 128*h + 2*tg + l.
+template <typename T, bool VEC>
+__device__ __forceinline__ void load_tile(T (&v)[64], const T *__restrict__ rowp, int64_t n,
+                                          int64_t jh, int tg, uint64_t sw) {
+    const int64_t base = jh * TILE + 2 * tg;
+    if (VEC && (jh + 1) * (int64_t)TILE <= n) {
+#pragma unroll
+        for (int h = 0; h < 32; ++h) Elem<T>::load2(rowp + base + 128 * h, v[2 * h], v[2 * h + 1]);
+    } else {
+#pragma unroll
+        for (int h = 0; h < 32; ++h) {
+            int64_t e = base + 128 * h;
+            v[2 * h] = (e < n) ? Elem<T>::load1(rowp + e) : T(0);
+            v[2 * h + 1] = (e + 1 < n) ? Elem<T>::load1(rowp + e + 1) : T(0);
+        }
+    }
+    const uint32_t lo = (uint32_t)sw, hi = (uint32_t)(sw >> 32);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        v[r] = xor_sign(v[r], lo << (31 - r));
+        v[r + 32] = xor_sign(v[r + 32], hi << (31 - r));
+    }
+}
+
+// Full 12-stage transform of one tile by a 64-thread group; result left in `buf`
+// at tile_pos().  Caller must __syncthreads() before other threads read buf.
+template <typename T>
+__device__ __forceinline__ void tile_fwht(T (&v)[64], T *__restrict__ buf, int tg) {
+    constexpr int M = Elem<T>::MASK;
+    butterflies64(v);  // bits 0, 7..11
+#pragma unroll
+    for (int r = 0; r < 64; ++r) buf[r * 64 + (tg ^ (r & M))] = v[r];
+    __syncthreads();
+    // round 2: thread tg holds B = tg, registers run over A
+#pragma unroll
+    for (int r = 0; r < 64; ++r) v[r] = buf[tg * 64 + (r ^ (tg & M))];
+    butterflies64(v);  // bits 1..6
+#pragma unroll
+    for (int r = 0; r < 64; ++r) buf[tg * 64 + (r ^ (tg & M))] = v[r];
+}
+
+template <typename T>
+struct SrhtArgs {
+    const T *x;
+    int64_t ldx, n;
+    int64_t m;
+    const uint64_t *signw;   // [ntiles_valid][64]
+    const uint32_t *desc;    // [NSLOT][128]   bits 0..11 tile_pos(sl), bits 12..31 sh
+    T *ws;                   // [nchunks][m][NSLOT*128]
+    int log2L;               // tiles per CTA = 2^log2L (>= 2)
+    int64_t nchunks;         // chunks per row actually launched
+    int64_t ntiles_valid;    // tiles that contain at least one element < n
+};
+
+template <typename T, int NSLOT, bool VEC>
+__global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const int tid = threadIdx.x, grp = tid >> 6, tg = tid & 63;
+    const int64_t row = blockIdx.x / a.nchunks;
+    const int64_t chunk = blockIdx.x % a.nchunks;
+    const int64_t c0 = chunk << a.log2L;
+    const int npairs = 1 << (a.log2L - 1);
+    const T *rowp = a.x + row * a.ldx;
+    T *buf = sm + grp * TILE;
+
+    T acc[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) acc[s] = T(0);
+
+    for (int u = 0; u < npairs; ++u) {
+        const int g = u ^ (u >> 1);
+        const int64_t jhA = c0 + 2 * (int64_t)g;
+        const int64_t jh = jhA + grp;
+        // sign flip when moving from pair u-1 to pair u: bit (ctz(u)+1) of sh = desc bit 13+ctz(u)
+        const int fl_shift = 31 - (13 + (u ? __ffs(u) - 1 : 0));
+        if (jhA < a.ntiles_valid) {
+            T v[64];
+            if (jh < a.ntiles_valid) {
+                const uint64_t sw = __ldg(a.signw + jh * GROUP + tg);
+                load_tile<T, VEC>(v, rowp, a.n, jh, tg, sw);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 64; ++r) v[r] = T(0);
+            }
+            tile_fwht(v, buf, tg);
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+                const uint32_t dsc = __ldg(a.desc + s * CTA + tid);
+                const int off = dsc & (TILE - 1);
+                const T vA = sm[off], vB = sm[TILE + off];
+                const T w = vA + xor_sign(vB, dsc << 19);        // bit 12 = sh bit 0
+                acc[s] = xor_sign(acc[s], dsc << fl_shift) + w;
+            }
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+                const uint32_t dsc = __ldg(a.desc + s * CTA + tid);
+                acc[s] = xor_sign(acc[s], dsc << fl_shift);
+            }
+        }
+    }
+    // accumulators are relative to the sign of the last A tile: undo it
+    const int glast = (npairs - 1) ^ ((npairs - 1) >> 1);
+    const uint32_t jlast = (uint32_t)(c0 + 2 * (int64_t)glast);
+    T *wsp = a.ws + ((chunk * a.m + row) * (int64_t)(NSLOT * CTA));
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const uint32_t dsc = __ldg(a.desc + s * CTA + tid);
+        const uint32_t par = __popc((dsc >> TILE_LOG2) & jlast) & 1u;
+        wsp[s * CTA + tid] = xor_sign(acc[s], par << 31);
+    }
+}
+
+// y[row, i] = scale * sum_chunks ws[pass(i)][chunk][row][slot(i)]
+template <typename T>
+__global__ void srht_finalize_kernel(const T *__restrict__ ws, const int32_t *__restrict__ slotmap,
+                                     T *__restrict__ y, int64_t ldy, int64_t k, int64_t m,
+                                     int64_t nchunks, int nst, int64_t pass_stride, T scale) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t row = blockIdx.y;
+    if (i >= k) return;
+    const int32_t sm = slotmap[i];
+    const int pass = sm / nst, slot = sm % nst;
+    const T *p = ws + pass * pass_stride + row * nst + slot;
+    T s = T(0);
+    for (int64_t q = 0; q < nchunks; ++q) s += p[q * m * nst];
+    y[row * ldy + i] = scale * s;
+}
+
+}  // namespace rla
+
+using namespace rla;
+
+struct rla_srht_plan {
+    int64_t n = 0, k = 0;
+    int d = 0;
+    int elem_bytes = 8;
+    int64_t ntiles = 0;        // padded tiles per row (>= 2)
+    int64_t ntiles_valid = 0;
+    int nslot = 0;             // accumulators per thread (4, 8, 16 or 32)
+    int npass = 1;
+    int64_t nuniq = 0;
+    size_t off_sign = 0, off_desc = 0, off_slot = 0;
+    std::vector<unsigned char> image;
+    const unsigned char *dev = nullptr;
+};
+
+static size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+extern "C" int rla_srht_plan_create(rla_srht_plan **out, const int8_t *signs, int64_t n,
+                                    const int64_t *idx, int64_t k, int elem_bytes) {
+    RLA_REQUIRE(out && signs && (idx || k == 0), "rla_srht_plan_create: null argument");
+    RLA_REQUIRE(n >= 1 && k >= 0, "rla_srht_plan_create: need n >= 1, k >= 0 (n=%lld k=%lld)", (long long)n, (long long)k);
+    RLA_REQUIRE(elem_bytes == 8 || elem_bytes == 4, "rla_srht_plan_create: elem_bytes must be 8 or 4");
+    const int d = ceil_log2_i64(n);
+    RLA_REQUIRE(d <= 31, "rla_srht_plan_create: n too large (d=%d > 31)", d);
+    const int64_t np2 = int64_t(1) << d;
+    for (int64_t i = 0; i < k; ++i)
+        RLA_REQUIRE(idx[i] >= 0 && idx[i] < np2, "rla_srht_plan_create: idx[%lld]=%lld outside [0, 2^%d)",
+                    (long long)i, (long long)idx[i], d);
+    rla_srht_plan *p = new (std::nothrow) rla_srht_plan;
+    RLA_REQUIRE(p, "out of host memory");
+    p->n = n; p->k = k; p->d = d; p->elem_bytes = elem_bytes;
+    const int dp = std::max(d, TILE_LOG2 + 1);
+    p->ntiles = int64_t(1) << (dp - TILE_LOG2);
+    p->ntiles_valid = (n + TILE - 1) / TILE;
+    const int mask = elem_bytes == 8 ? 15 : 31;
+    const int lanes = mask + 1;                // lanes per shared-memory wavefront
+    // distinct sample values
+    std::vector<int64_t> uniq(idx, idx + k);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    p->nuniq = (int64_t)uniq.size();
+    p->npass = (int)std::max<int64_t>(1, (p->nuniq + MAX_SLOTS - 1) / MAX_SLOTS);
+    const int64_t per_pass = (p->nuniq + p->npass - 1) / p->npass;
+    int nslot = 4;
+    while ((int64_t)nslot * CTA < per_pass) nslot *= 2;
+    p->nslot = nslot;
+    const int nst = nslot * CTA;
+    p->off_sign = 0;
+    p->off_desc = align16(p->off_sign + (size_t)p->ntiles_valid * GROUP * 8);
+    p->off_slot = align16(p->off_desc + (size_t)p->npass * nst * 4);
+    p->image.assign(align16(p->off_slot + (size_t)std::max<int64_t>(k, 1) * 4), 0);
+    // packed sign bits: word [jh*64 + tg], bit rho=2h+l <-> element jh*4096 + 128h + 2tg + l
+    uint64_t *sw = reinterpret_cast<uint64_t *>(p->image.data() + p->off_sign);
+    for (int64_t j = 0; j < n; ++j) {
+        if (signs[j] < 0) {
+            const int64_t jh = j >> TILE_LOG2;
+            const int e = (int)(j & (TILE - 1));
+            const int h = e >> 7, tg = (e >> 1) & 63, l = e & 1;
+            sw[jh * GROUP + tg] |= uint64_t(1) << (2 * h + l);
+        }
+    }
+    // slot assignment: lane (tid % lanes) should equal the bank group of the gathered word
+    uint32_t *desc = reinterpret_cast<uint32_t *>(p->image.data() + p->off_desc);
+    std::vector<int32_t> slot_of_uniq(uniq.size());
+    const int threads_per_bucket = CTA / lanes;
+    for (int pass = 0; pass < p->npass; ++pass) {
+        const int64_t u0 = pass * per_pass, u1 = std::min<int64_t>(p->nuniq, u0 + per_pass);
+        std::vector<int> cnt(lanes, 0);
+        std::vector<char> used(nst, 0);
+        std::vector<int64_t> overflow;
+        const int cap = nslot * threads_per_bucket;
+        for (int64_t u = u0; u < u1; ++u) {
+            const int pos = tile_pos((int)(uniq[u] & (TILE - 1)), mask);
+            const int b = pos & mask;
+            if (cnt[b] < cap) {
+                const int c = cnt[b]++;
+                const int tid = b + lanes * (c % threads_per_bucket), s = c / threads_per_bucket;
+                const int cell = s * CTA + tid;
+                used[cell] = 1;
+                desc[(size_t)pass * nst + cell] = (uint32_t)pos | ((uint32_t)(uniq[u] >> TILE_LOG2) << TILE_LOG2);
+                slot_of_uniq[u] = pass * nst + cell;
+            } else {
+                overflow.push_back(u);
+            }
+        }
+        int cell = 0;
+        for (int64_t u : overflow) {
+            while (used[cell]) ++cell;
+            used[cell] = 1;
+            const int pos = tile_pos((int)(uniq[u] & (TILE - 1)), mask);
+            desc[(size_t)pass * nst + cell] = (uint32_t)pos | ((uint32_t)(uniq[u] >> TILE_LOG2) << TILE_LOG2);
+            slot_of_uniq[u] = pass * nst + cell;
+        }
+    }
+    int32_t *slotmap = reinterpret_cast<int32_t *>(p->image.data() + p->off_slot);
+    for (int64_t i = 0; i < k; ++i) {
+        const size_t u = std::lower_bound(uniq.begin(), uniq.end(), idx[i]) - uniq.begin();
+        slotmap[i] = slot_of_uniq[u];
+    }
+    *out = p;
+    return RLA_OK;
+}
+
+extern "C" void rla_srht_plan_destroy(rla_srht_plan *p) { delete p; }
+extern "C" size_t rla_srht_plan_device_bytes(const rla_srht_plan *p) { return p ? p->image.size() : 0; }
+extern "C" int rla_srht_plan_passes(const rla_srht_plan *p) { return p ? p->npass : 0; }
+
+extern "C" int rla_srht_plan_upload(rla_srht_plan *p, void *plan_dev, void *stream) {
+    RLA_REQUIRE(p && plan_dev, "rla_srht_plan_upload: null argument");
+    RLA_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 15) == 0, "rla_srht_plan_upload: buffer must be 16-byte aligned");
+    RLA_CUDA_CHECK(cudaMemcpyAsync(plan_dev, p->image.data(), p->image.size(), cudaMemcpyHostToDevice,
+                                   (cudaStream_t)stream));
+    RLA_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));   // image is pageable host memory
+    p->dev = static_cast<const unsigned char *>(plan_dev);
+    return RLA_OK;
+}
+
+// tiles per CTA: enough CTAs for >= 16 waves when the problem is large, but at least
+// 4 tiles per CTA so the partial-sketch write stays small next to the tile reads.
+static int choose_log2L(const rla_srht_plan *p, int64_t m) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("RLA_SRHT_LOG2L");
+        forced = e ? atoi(e) : -1;
+    }
+    int maxl = 0;
+    while ((int64_t(1) << (maxl + 1)) <= p->ntiles) ++maxl;
+    if (forced >= 1) return std::min(forced, maxl);
+    const int64_t target = (int64_t)sm_count() * 2 * 16;
+    const int64_t total = m * p->ntiles_valid;
+    int l = 1;
+    while (l < maxl && (total >> (l + 1)) >= target) ++l;
+    if (l < 2 && maxl >= 2) l = 2;
+    return l;
+}
+
+static int64_t valid_chunks(const rla_srht_plan *p, int log2L) {
+    const int64_t L = int64_t(1) << log2L;
+    return (p->ntiles_valid + L - 1) / L;
+}
+
+extern "C" size_t rla_srht_workspace_bytes(const rla_srht_plan *p, int64_t m) {
+    if (!p || m <= 0) return 0;
+    // the chunk count depends on m only through choose_log2L; take the max over the two
+    // extreme choices so that a forced/tuned L never overflows the buffer
+    const int64_t nch = valid_chunks(p, choose_log2L(p, m));
+    return (size_t)p->npass * nch * m * p->nslot * CTA * p->elem_bytes;
+}
+
+template <typename T, int NSLOT, bool VEC>
+static int launch_main(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
+    auto kern = srht_main_kernel<T, NSLOT, VEC>;
+    const int smem = 2 * TILE * sizeof(T);
+    RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)grid, CTA, smem, st>>>(a);
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
+
+template <typename T, bool VEC>
+static int dispatch_nslot(int nslot, const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
+    switch (nslot) {
+        case 4: return launch_main<T, 4, VEC>(a, grid, st);
+        case 8: return launch_main<T, 8, VEC>(a, grid, st);
+        case 16: return launch_main<T, 16, VEC>(a, grid, st);
+        case 32: return launch_main<T, 32, VEC>(a, grid, st);
+    }
+    return fail(RLA_ERR_INVALID, "srht: bad nslot %d", nslot);
+}
+
+template <typename T>
+static int srht_apply(const rla_srht_plan *p, const T *x, int64_t m, int64_t ldx, T scale, T *y,
+                      int64_t ldy, void *ws, size_t ws_bytes, void *stream) {
+    RLA_REQUIRE(p && p->dev, "rla_srht_apply: plan not uploaded");
+    RLA_REQUIRE(p->elem_bytes == (int)sizeof(T), "rla_srht_apply: plan was built for %d-byte elements", p->elem_bytes);
+    RLA_REQUIRE(m >= 0 && ldx >= p->n && ldy >= p->k, "rla_srht_apply: bad m/ldx/ldy");
+    if (m == 0 || p->k == 0) return RLA_OK;
+    RLA_REQUIRE(x && y && ws, "rla_srht_apply: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int log2L = choose_log2L(p, m);
+    const int64_t nch = valid_chunks(p, log2L);
+    const int nst = p->nslot * CTA;
+    const size_t need = (size_t)p->npass * nch * m * nst * sizeof(T);
+    if (ws_bytes < need) return fail(RLA_ERR_WORKSPACE, "rla_srht_apply: workspace %zu < %zu bytes", ws_bytes, need);
+    const int64_t grid = m * nch;
+    RLA_REQUIRE(grid < (int64_t(1) << 31), "rla_srht_apply: grid too large");
+    const bool vec = (reinterpret_cast<uintptr_t>(x) % (2 * sizeof(T)) == 0) && (ldx % 2 == 0);
+    for (int pass = 0; pass < p->npass; ++pass) {
+        SrhtArgs<T> a;
+        a.x = x; a.ldx = ldx; a.n = p->n; a.m = m;
+        a.signw = reinterpret_cast<const uint64_t *>(p->dev + p->off_sign);
+        a.desc = reinterpret_cast<const uint32_t *>(p->dev + p->off_desc) + (size_t)pass * nst;
+        a.ws = static_cast<T *>(ws) + (size_t)pass * nch * m * nst;
+        a.log2L = log2L; a.nchunks = nch; a.ntiles_valid = p->ntiles_valid;
+        int rc = vec ? dispatch_nslot<T, true>(p->nslot, a, grid, st) : dispatch_nslot<T, false>(p->nslot, a, grid, st);
+        if (rc != RLA_OK) return rc;
+    }
+    const int fin_threads = 256;
+    dim3 fgrid((unsigned)((p->k + fin_threads - 1) / fin_threads), 1, 1);
+    // gridDim.y is limited to 65535: loop over row blocks
+    for (int64_t r0 = 0; r0 < m; r0 += 65535) {
+        const int64_t rows = std::min<int64_t>(65535, m - r0);
+        fgrid.y = (unsigned)rows;
+        srht_finalize_kernel<T><<<fgrid, fin_threads, 0, st>>>(
+            static_cast<const T *>(ws) + r0 * nst, reinterpret_cast<const int32_t *>(p->dev + p->off_slot),
+            y + r0 * ldy, ldy, p->k, m, nch, nst, (int64_t)nch * m * nst, scale);
+    }
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
+
+extern "C" int rla_srht_apply_f64(const rla_srht_plan *p, const double *x, int64_t m, int64_t ldx,
+                                  double scale, double *y, int64_t ldy, void *ws, size_t ws_bytes, void *stream) {
+    return srht_apply<double>(p, x, m, ldx, scale, y, ldy, ws, ws_bytes, stream);
+}
+extern "C" int rla_srht_apply_f32(const rla_srht_plan *p, const float *x, int64_t m, int64_t ldx,
+                                  float scale, float *y, int64_t ldy, void *ws, size_t ws_bytes, void *stream) {
+    return srht_apply<float>(p, x, m, ldx, scale, y, ldy, ws, ws_bytes, stream);
+}
+
+// ------------------------------------------------------------- explicit rows
+namespace rla {
+__global__ void srht_rows_kernel(const int8_t *__restrict__ signs, int64_t n, const int64_t *__restrict__ idx,
+                                 const int64_t *__restrict__ rows, double value, double *__restrict__ out,
+                                 int64_t ldo) {
+    const int64_t i = blockIdx.y;
+    const uint32_t s = (uint32_t)idx[rows[i]];
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t par = (__popc(s & (uint32_t)j) & 1u) ^ (signs[j] < 0 ? 1u : 0u);
+        out[i * ldo + j] = par ? -value : value;
+    }
+}
+}  // namespace rla
+
+extern "C" int rla_srht_rows_f64(const int8_t *signs, int64_t n, const int64_t *idx, const int64_t *rows,
+                                 int64_t nrows, double value, double *out, int64_t ldo, void *stream) {
+    RLA_REQUIRE(n >= 1 && nrows >= 0 && ldo >= n, "rla_srht_rows_f64: bad sizes");
+    if (nrows == 0) return RLA_OK;
+    RLA_REQUIRE(signs && idx && rows && out, "rla_srht_rows_f64: null pointer");
+    for (int64_t r0 = 0; r0 < nrows; r0 += 65535) {
+        const int64_t nr = std::min<int64_t>(65535, nrows - r0);
+        dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 4096), (unsigned)nr);
+        srht_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(signs, n, idx, rows + r0, value, out + r0 * ldo, ldo);
+    }
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
