@@ -80,23 +80,41 @@ __device__ __forceinline__ void butterflies64(T (&v)[64]) {
     }
 }
 
-// Sign-flipped load of one tile into the round-1 register layout:
+// 64-thread barrier of one tile group (ids 1 and 2; id 0 is __syncthreads)
+__device__ __forceinline__ void group_barrier(int grp) {
+    if (grp == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else asm volatile("bar.sync 2, 64;" ::: "memory");
+}
+
+// Fast load of a full, 16-byte aligned tile straight into the round-1 register layout:
 // register rho = 2*h + l  <->  tile element e = 128*h + 2*tg + l.
-template <typename T, bool VEC>
-__device__ __forceinline__ void load_tile(T (&v)[64], const T *__restrict__ rowp, int64_t n,
-                                          int64_t jh, int tg, uint64_t sw) {
-    const int64_t base = jh * TILE + 2 * tg;
-    if (VEC && (jh + 1) * (int64_t)TILE <= n) {
+template <typename T>
+__device__ __forceinline__ void load_tile_fast(T (&v)[64], const T *__restrict__ tilep, int tg) {
 #pragma unroll
-        for (int h = 0; h < 32; ++h) Elem<T>::load2(rowp + base + 128 * h, v[2 * h], v[2 * h + 1]);
-    } else {
+    for (int h = 0; h < 32; ++h) Elem<T>::load2(tilep + 128 * h + 2 * tg, v[2 * h], v[2 * h + 1]);
+}
+
+// Slow load (ragged last tile, or rows that are not 16-byte aligned): stage the tile in
+// natural order through the group's shared-memory buffer; elements at or beyond n read
+// as zero (the virtual zero padding of srht.py:167).
+template <typename T>
+__device__ __forceinline__ void load_tile_slow(T (&v)[64], const T *__restrict__ rowp, int64_t n,
+                                               int64_t jh, int tg, T *__restrict__ buf, int grp) {
+    const int64_t j0 = jh * TILE;
+#pragma unroll 4
+    for (int e = tg; e < TILE; e += GROUP) buf[e] = (j0 + e < n) ? Elem<T>::load1(rowp + j0 + e) : T(0);
+    group_barrier(grp);
 #pragma unroll
-        for (int h = 0; h < 32; ++h) {
-            int64_t e = base + 128 * h;
-            v[2 * h] = (e < n) ? Elem<T>::load1(rowp + e) : T(0);
-            v[2 * h + 1] = (e + 1 < n) ? Elem<T>::load1(rowp + e + 1) : T(0);
-        }
+    for (int h = 0; h < 32; ++h) {
+        v[2 * h] = buf[128 * h + 2 * tg];
+        v[2 * h + 1] = buf[128 * h + 2 * tg + 1];
     }
+    group_barrier(grp);
+}
+
+// Rademacher sign flip (srht.py:165) from the packed sign word of this thread.
+template <typename T>
+__device__ __forceinline__ void flip_signs(T (&v)[64], uint64_t sw) {
     const uint32_t lo = (uint32_t)sw, hi = (uint32_t)(sw >> 32);
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
@@ -106,14 +124,17 @@ __device__ __forceinline__ void load_tile(T (&v)[64], const T *__restrict__ rowp
 }
 
 // Full 12-stage transform of one tile by a 64-thread group; result left in `buf`
-// at tile_pos().  Caller must __syncthreads() before other threads read buf.
+// at tile_pos().  Caller must synchronise before other threads read buf.
 template <typename T>
-__device__ __forceinline__ void tile_fwht(T (&v)[64], T *__restrict__ buf, int tg) {
+__device__ __forceinline__ void tile_fwht(T (&v)[64], T *__restrict__ buf, int tg, int grp) {
     constexpr int M = Elem<T>::MASK;
+    // opaque copy: keeps the compiler from hoisting the 64 swizzled addresses out of the
+    // tile loop (they would not fit in registers and end up in local memory)
+    asm volatile("" : "+r"(tg));
     butterflies64(v);  // bits 0, 7..11
 #pragma unroll
     for (int r = 0; r < 64; ++r) buf[r * 64 + (tg ^ (r & M))] = v[r];
-    __syncthreads();
+    group_barrier(grp);
     // round 2: thread tg holds B = tg, registers run over A
 #pragma unroll
     for (int r = 0; r < 64; ++r) v[r] = buf[tg * 64 + (r ^ (tg & M))];
@@ -131,11 +152,12 @@ struct SrhtArgs {
     const uint32_t *desc;    // [NSLOT][128]   bits 0..11 tile_pos(sl), bits 12..31 sh
     T *ws;                   // [nchunks][m][NSLOT*128]
     int log2L;               // tiles per CTA = 2^log2L (>= 2)
+    int aligned;             // rows are 16-byte aligned: full tiles take the fast load
     int64_t nchunks;         // chunks per row actually launched
     int64_t ntiles_valid;    // tiles that contain at least one element < n
 };
 
-template <typename T, int NSLOT, bool VEC>
+template <typename T, int NSLOT, bool PF>
 __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
@@ -146,31 +168,58 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
     const int npairs = 1 << (a.log2L - 1);
     const T *rowp = a.x + row * a.ldx;
     T *buf = sm + grp * TILE;
+    // sample descriptors of this thread live in shared memory (behind the two tile
+    // buffers) so the gather never queues behind in-flight tile loads
+    uint32_t *sdesc = reinterpret_cast<uint32_t *>(sm + 2 * TILE) + tid;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) sdesc[s * CTA] = __ldg(a.desc + s * CTA + tid);
 
     T acc[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) acc[s] = T(0);
 
+    // tile of this group in pair u (Gray-code order); valid tiles form a prefix
+    auto tile_of = [&](int u) -> int64_t { return c0 + 2 * (int64_t)(u ^ (u >> 1)) + grp; };
+    auto is_fast = [&](int64_t jh) -> bool { return a.aligned && (jh + 1) * (int64_t)TILE <= a.n; };
+
+    T v[64];
+    uint64_t sw = 0;
+    if (PF) {   // prologue: loads of pair 0
+        const int64_t jh = tile_of(0);
+        if (jh < a.ntiles_valid) {
+            sw = __ldg(a.signw + jh * GROUP + tg);
+            if (is_fast(jh)) load_tile_fast(v, rowp + jh * TILE, tg);
+        }
+    }
     for (int u = 0; u < npairs; ++u) {
-        const int g = u ^ (u >> 1);
-        const int64_t jhA = c0 + 2 * (int64_t)g;
+        const int64_t jhA = c0 + 2 * (int64_t)(u ^ (u >> 1));
         const int64_t jh = jhA + grp;
         // sign flip when moving from pair u-1 to pair u: bit (ctz(u)+1) of sh = desc bit 13+ctz(u)
         const int fl_shift = 31 - (13 + (u ? __ffs(u) - 1 : 0));
         if (jhA < a.ntiles_valid) {
-            T v[64];
             if (jh < a.ntiles_valid) {
-                const uint64_t sw = __ldg(a.signw + jh * GROUP + tg);
-                load_tile<T, VEC>(v, rowp, a.n, jh, tg, sw);
+                if (!PF) sw = __ldg(a.signw + jh * GROUP + tg);
+                if (!is_fast(jh)) load_tile_slow(v, rowp, a.n, jh, tg, buf, grp);
+                else if (!PF) load_tile_fast(v, rowp + jh * TILE, tg);
+                flip_signs(v, sw);
             } else {
 #pragma unroll
                 for (int r = 0; r < 64; ++r) v[r] = T(0);
             }
-            tile_fwht(v, buf, tg);
+            tile_fwht(v, buf, tg, grp);
             __syncthreads();
+            // v is dead and its write-back is ordered before the barrier: start the loads
+            // of the next pair now so they fly during the gather
+            if (PF && u + 1 < npairs) {
+                const int64_t jn = tile_of(u + 1);
+                if (jn < a.ntiles_valid) {
+                    sw = __ldg(a.signw + jn * GROUP + tg);
+                    if (is_fast(jn)) load_tile_fast(v, rowp + jn * TILE, tg);
+                }
+            }
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
-                const uint32_t dsc = __ldg(a.desc + s * CTA + tid);
+                const uint32_t dsc = sdesc[s * CTA];
                 const int off = dsc & (TILE - 1);
                 const T vA = sm[off], vB = sm[TILE + off];
                 const T w = vA + xor_sign(vB, dsc << 19);        // bit 12 = sh bit 0
@@ -180,7 +229,7 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
         } else {
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
-                const uint32_t dsc = __ldg(a.desc + s * CTA + tid);
+                const uint32_t dsc = sdesc[s * CTA];
                 acc[s] = xor_sign(acc[s], dsc << fl_shift);
             }
         }
@@ -191,7 +240,7 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
     T *wsp = a.ws + ((chunk * a.m + row) * (int64_t)(NSLOT * CTA));
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
-        const uint32_t dsc = __ldg(a.desc + s * CTA + tid);
+        const uint32_t dsc = sdesc[s * CTA];
         const uint32_t par = __popc((dsc >> TILE_LOG2) & jlast) & 1u;
         wsp[s * CTA + tid] = xor_sign(acc[s], par << 31);
     }
@@ -365,23 +414,38 @@ extern "C" size_t rla_srht_workspace_bytes(const rla_srht_plan *p, int64_t m) {
     return (size_t)p->npass * nch * m * p->nslot * CTA * p->elem_bytes;
 }
 
-template <typename T, int NSLOT, bool VEC>
-static int launch_main(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
-    auto kern = srht_main_kernel<T, NSLOT, VEC>;
-    const int smem = 2 * TILE * sizeof(T);
+static bool use_prefetch() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RLA_SRHT_PREFETCH");
+        v = e ? atoi(e) : 0;
+    }
+    return v != 0;
+}
+
+template <typename T, int NSLOT, bool PF>
+static int launch_main_pf(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
+    auto kern = srht_main_kernel<T, NSLOT, PF>;
+    const int smem = 2 * TILE * sizeof(T) + NSLOT * CTA * 4;
     RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(unsigned)grid, CTA, smem, st>>>(a);
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;
 }
 
-template <typename T, bool VEC>
+template <typename T, int NSLOT>
+static int launch_main(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
+    return use_prefetch() ? launch_main_pf<T, NSLOT, true>(a, grid, st)
+                          : launch_main_pf<T, NSLOT, false>(a, grid, st);
+}
+
+template <typename T>
 static int dispatch_nslot(int nslot, const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
     switch (nslot) {
-        case 4: return launch_main<T, 4, VEC>(a, grid, st);
-        case 8: return launch_main<T, 8, VEC>(a, grid, st);
-        case 16: return launch_main<T, 16, VEC>(a, grid, st);
-        case 32: return launch_main<T, 32, VEC>(a, grid, st);
+        case 4: return launch_main<T, 4>(a, grid, st);
+        case 8: return launch_main<T, 8>(a, grid, st);
+        case 16: return launch_main<T, 16>(a, grid, st);
+        case 32: return launch_main<T, 32>(a, grid, st);
     }
     return fail(RLA_ERR_INVALID, "srht: bad nslot %d", nslot);
 }
@@ -409,8 +473,8 @@ static int srht_apply(const rla_srht_plan *p, const T *x, int64_t m, int64_t ldx
         a.signw = reinterpret_cast<const uint64_t *>(p->dev + p->off_sign);
         a.desc = reinterpret_cast<const uint32_t *>(p->dev + p->off_desc) + (size_t)pass * nst;
         a.ws = static_cast<T *>(ws) + (size_t)pass * nch * m * nst;
-        a.log2L = log2L; a.nchunks = nch; a.ntiles_valid = p->ntiles_valid;
-        int rc = vec ? dispatch_nslot<T, true>(p->nslot, a, grid, st) : dispatch_nslot<T, false>(p->nslot, a, grid, st);
+        a.log2L = log2L; a.nchunks = nch; a.ntiles_valid = p->ntiles_valid; a.aligned = vec ? 1 : 0;
+        int rc = dispatch_nslot<T>(p->nslot, a, grid, st);
         if (rc != RLA_OK) return rc;
     }
     const int fin_threads = 256;
