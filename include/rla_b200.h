@@ -39,6 +39,9 @@ typedef enum rla_status {
 
 int rla_version(void);
 const char *rla_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports
+ * the delta over its timed region as "gpu_launches") */
+unsigned long long rla_launch_count(void);
 
 /* ------------------------------------------------------------------ SRHT ---
  * Replaces srht(x, k, seed, nthreads)            rla/srht.py:136-177
@@ -100,9 +103,12 @@ int rla_fwht_f32(const float *a_dev, int64_t m, int64_t n_pow2, int64_t lda,
 /* Adjoint of the SRHT rows matrix without materialising it
  * (replaces the dense GEMM of SrhtEmbedding.apply_adjoint, rla/embeddings.py:175-178):
  *   out[c, j] = value * signs[j] * sum_i (-1)^popcount(idx[i] & j) * v[c, i],  j < n
- * scratch: m * 2**d elements (rla_srht_adjoint_workspace_bytes). */
+ * order_dev: int32 permutation of [0, k) sorting idx ascending (stable), so duplicate
+ * indices are summed in sample order.  scratch: m * 2**d elements
+ * (rla_srht_adjoint_workspace_bytes). */
 size_t rla_srht_adjoint_workspace_bytes(int64_t m, int64_t n);
-int rla_srht_adjoint_f64(const int8_t *signs_dev, int64_t n, const int64_t *idx_dev, int64_t k,
+int rla_srht_adjoint_f64(const int8_t *signs_dev, int64_t n, const int64_t *idx_dev,
+                         const int32_t *order_dev, int64_t k,
                          const double *v_dev, int64_t m, int64_t ldv, double value,
                          double *out_dev, int64_t ldo, void *ws_dev, size_t ws_bytes, void *stream);
 

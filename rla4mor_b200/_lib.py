@@ -21,6 +21,7 @@ _vp = c_void_p
 _SIGS = {
     "rla_version": (c_int, []),
     "rla_last_error": (c_char_p, []),
+    "rla_launch_count": (ctypes.c_ulonglong, []),
     "rla_srht_plan_create": (c_int, [POINTER(c_void_p), _vp, c_int64, _vp, c_int64, c_int]),
     "rla_srht_plan_destroy": (None, [_vp]),
     "rla_srht_plan_device_bytes": (c_size_t, [_vp]),
@@ -33,7 +34,7 @@ _SIGS = {
     "rla_fwht_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, c_int64, c_double, _vp]),
     "rla_fwht_f32": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, c_int64, c_float, _vp]),
     "rla_srht_adjoint_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "rla_srht_adjoint_f64": (c_int, [_vp, c_int64, _vp, c_int64, _vp, c_int64, c_int64, c_double, _vp, c_int64,
+    "rla_srht_adjoint_f64": (c_int, [_vp, c_int64, _vp, _vp, c_int64, _vp, c_int64, c_int64, c_double, _vp, c_int64,
                                      _vp, c_size_t, _vp]),
     "rla_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rla_gauss_apply_explicit_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, c_int64, c_int64, _vp, c_int64,

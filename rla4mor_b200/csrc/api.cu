@@ -25,5 +25,11 @@ int sm_count() {
 }
 }  // namespace rla
 
+namespace rla {
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+}  // namespace rla
+
 extern "C" int rla_version(void) { return 100; }
+extern "C" unsigned long long rla_launch_count(void) { return __atomic_load_n(&rla::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char *rla_last_error(void) { return rla::g_err; }

@@ -41,6 +41,8 @@ inline int ceil_log2_i64(int64_t n) {   // d = int(ceil(log2(n))), n >= 1
 
 // number of SMs of the current device (cached)
 int sm_count();
+// bookkeeping for rla_launch_count(): every kernel launch of this library is counted
+void count_launch(int n = 1);
 
 // streaming 16-byte / 8-byte global loads that do not allocate in L1
 __device__ __forceinline__ double2 ldg_stream_f64x2(const double *p) {

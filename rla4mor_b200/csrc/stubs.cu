@@ -4,11 +4,6 @@
 #define RLA_STUB(name) return ::rla::fail(RLA_ERR_UNSUPPORTED, name ": not implemented yet")
 
 extern "C" {
-int rla_fwht_f64(const double *, int64_t, int64_t, int64_t, double *, int64_t, double, void *) { RLA_STUB("rla_fwht_f64"); }
-int rla_fwht_f32(const float *, int64_t, int64_t, int64_t, float *, int64_t, float, void *) { RLA_STUB("rla_fwht_f32"); }
-size_t rla_srht_adjoint_workspace_bytes(int64_t, int64_t) { return 0; }
-int rla_srht_adjoint_f64(const int8_t *, int64_t, const int64_t *, int64_t, const double *, int64_t, int64_t, double,
-                         double *, int64_t, void *, size_t, void *) { RLA_STUB("rla_srht_adjoint_f64"); }
 size_t rla_gemm_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
 int rla_gauss_apply_explicit_f64(const double *, int64_t, int64_t, int64_t, const double *, int64_t, int64_t,
                                  double *, int64_t, void *, size_t, void *) { RLA_STUB("rla_gauss_apply_explicit_f64"); }
