@@ -1,0 +1,425 @@
+// gemm.cu -- dense embeddings:  Y(m, k) = U(m, n) * Theta(k, n)^T  in FP64 on the
+// tensor pipe (DMMA), fed by TMA, with Theta either resident in HBM (explicit) or
+// generated on the fly in registers from the counter-based RNG of rng.cuh.
+//
+// Replaces NumpyMatrixOperator(Theta).apply(Q U) = (Theta @ (QU)^T)^T of
+//   GaussianEmbedding.apply            rla/embeddings.py:250-254
+//   BlockGaussianEmbedding.apply       rla/embeddings.py:425-434 (one call per row block)
+//
+// Structure (one CTA per SM, 8 consumer warps):
+//   * CTA tile  BM x BN  of Y over one chunk of the reduction dimension n (split-n:
+//     the k x m sketch is far too small to fill 148 SMs); per-chunk partial tiles go to
+//     a workspace and are summed in chunk order by a reduce kernel (deterministic).
+//   * U (and Theta when explicit) stream through a 4-stage shared-memory ring of
+//     [rows x 16 doubles] boxes written by TMA (cp.async.bulk.tensor, 128-byte swizzle,
+//     out-of-range rows/columns zero-filled by the TMA unit: ragged m, k, n for free).
+//   * warp tile 64 x 32: per 16-wide k block a thread reads, for each of its 8 row groups,
+//     the 4 consecutive doubles k = 4t..4t+3 (two conflict-free LDS.128) and issues
+//     mma.sync.m8n8k4.f64 for the 4 k sub-steps (the k permutation inside a block is
+//     free as long as A and B fragments agree).  Accumulators: 64 doubles per thread.
+//   * on-the-fly Theta: the B fragment of a thread is Theta[row = nbase+8i+g, 4t..4t+3]
+//     = exactly one Philox block -> 4 normals, produced in registers, never in memory.
+#include "common.cuh"
+#include "rng.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <algorithm>
+
+namespace rla {
+
+constexpr int GK = 16;                 // doubles per row per stage (128 bytes = swizzle span)
+constexpr int GSTAGES = 4;
+constexpr int GWARPS = 8;
+constexpr int GTHREADS = GWARPS * 32;
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// 4 consecutive doubles k = 4t..4t+3 of row `row` of a [rows][16] box stored with the
+// 128-byte TMA swizzle (16-byte chunk index XOR (row & 7))
+__device__ __forceinline__ void lds_row4(const double *tile, int row, int t, double (&v)[4]) {
+    const char *base = reinterpret_cast<const char *>(tile) + row * 128;
+    const int sw = row & 7;
+    const double2 lo = *reinterpret_cast<const double2 *>(base + (((2 * t) ^ sw) << 4));
+    const double2 hi = *reinterpret_cast<const double2 *>(base + (((2 * t + 1) ^ sw) << 4));
+    v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+}
+
+struct GemmArgs {
+    int64_t m, k, n;          // Y is m x k, reduction over n
+    int64_t kper;             // 16-wide k blocks per chunk
+    int64_t nchunks;
+    int mtiles, ntiles;       // tiles along m and along the sketch dimension
+    double *ws;               // [nchunks][m][k] partial sketches
+    uint64_t seed;            // RNG modes
+    int64_t row0, col0;       // offsets of this block inside the virtual Theta
+};
+
+// MODE 0: Theta explicit (second tensor map); 1: Philox normal; 2: Philox Rademacher
+template <int WM, int WN, int MODE>
+__global__ void __launch_bounds__(GTHREADS, 1)
+sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT, const GemmArgs a) {
+    constexpr int BM = WM * 64, BN = WN * 32;
+    static_assert(WM * WN == GWARPS, "8 warps");
+    constexpr int A_BYTES = BM * GK * 8;
+    constexpr int B_BYTES = (MODE == 0) ? BN * GK * 8 : 0;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[GSTAGES];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
+    // blockIdx.x = ntile + ntiles * (mtile + mtiles * chunk): CTAs sharing a U chunk are adjacent
+    int64_t b = blockIdx.x;
+    const int ntile = (int)(b % a.ntiles); b /= a.ntiles;
+    const int mtile = (int)(b % a.mtiles); b /= a.mtiles;
+    const int64_t chunk = b;
+    const int64_t kb0 = chunk * a.kper;
+    const int64_t nk16 = (a.n + GK - 1) / GK;
+    const int64_t kb1 = (kb0 + a.kper < nk16) ? kb0 + a.kper : nk16;
+    const int iters = (int)(kb1 - kb0);
+    const int m0 = mtile * BM, n0 = ntile * BN;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GSTAGES; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {   // thread 0 only
+        const int s = it % GSTAGES;
+        unsigned char *st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int x = (int)((kb0 + it) * GK);
+        tma_load_2d(st, &mapU, &full_bar[s], x, m0);
+        if (MODE == 0) tma_load_2d(st + A_BYTES, &mapT, &full_bar[s], x, n0);
+    };
+    if (tid == 0) {
+        for (int it = 0; it < GSTAGES - 1 && it < iters; ++it) issue(it);
+    }
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    // columns of the sketch (rows of Theta) owned by this thread's B fragments
+    const int ncol_base = n0 + wn * 32 + g;
+    // number of 8-wide column groups of this warp that fall inside the sketch (ragged k)
+    const int64_t ng64 = (a.k - (n0 + wn * 32) + 7) / 8;
+    const int ngroups = ng64 < 0 ? 0 : (ng64 > 4 ? 4 : (int)ng64);
+    // rows groups inside m
+    const int64_t mg64 = (a.m - (m0 + wm * 64) + 7) / 8;
+    const int mgroups = mg64 < 0 ? 0 : (mg64 > 8 ? 8 : (int)mg64);
+
+    for (int it = 0; it < iters; ++it) {
+        const int s = it % GSTAGES;
+        // slot (it-1) % S was released by the barrier at the end of the previous iteration
+        if (tid == 0 && it + GSTAGES - 1 < iters) issue(it + GSTAGES - 1);
+        // B fragments for this k block
+        double bf[4][4];
+        if (MODE != 0) {
+            const uint64_t q = (uint64_t)(a.col0 + (kb0 + it) * GK + 4 * t) >> 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < ngroups) {
+                    if (MODE == 1) theta4<0>(a.seed, (uint32_t)(a.row0 + ncol_base + 8 * j), q, bf[j]);
+                    else theta4<1>(a.seed, (uint32_t)(a.row0 + ncol_base + 8 * j), q, bf[j]);
+                }
+            }
+        }
+        mbar_wait(&full_bar[s], (it / GSTAGES) & 1);
+        const double *At = reinterpret_cast<const double *>(smem + s * STAGE_BYTES) + (wm * 64) * GK;
+        if (MODE == 0) {
+            const double *Bt = reinterpret_cast<const double *>(smem + s * STAGE_BYTES + A_BYTES) + (wn * 32) * GK;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lds_row4(Bt, 8 * j + g, t, bf[j]);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            double af[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) lds_row4(At, 8 * (4 * half + i) + g, t, af[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (4 * half + i < mgroups) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < ngroups) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                dmma884(acc[4 * half + i][j][0], acc[4 * half + i][j][1], af[i][kk], bf[j][kk]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with slot s; it is refilled next iteration
+    }
+
+    // partial tile -> workspace [chunk][m][k]
+    double *wsp = a.ws + chunk * a.m * a.k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t row = m0 + wm * 64 + 8 * i + g;
+        if (row >= a.m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t col = n0 + wn * 32 + 8 * j + 2 * t;
+            if (col < a.k) wsp[row * a.k + col] = acc[i][j][0];
+            if (col + 1 < a.k) wsp[row * a.k + col + 1] = acc[i][j][1];
+        }
+    }
+}
+
+// y[c, i] = (accumulate ? y[c, i] : 0) + scale * sum_chunks ws[chunk][c][i]
+__global__ void gemm_reduce_kernel(const double *__restrict__ ws, int64_t nchunks, int64_t m, int64_t k,
+                                   double scale, double *__restrict__ y, int64_t ldy, int accumulate) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= m * k) return;
+    const int64_t row = idx / k, col = idx % k;
+    double s = 0.0;
+    for (int64_t c = 0; c < nchunks; ++c) s += ws[c * m * k + idx];
+    double *dst = y + row * ldy + col;
+    *dst = accumulate ? (*dst + scale * s) : scale * s;
+}
+
+template <int KIND>
+__global__ void theta_materialize_kernel(uint64_t seed, double scale, int64_t row0, int64_t rows, int64_t col0,
+                                         int64_t cols, double *__restrict__ out, int64_t ldo) {
+    // one thread per aligned group of 4 columns
+    const int64_t q0 = col0 >> 2, q1 = (col0 + cols + 3) >> 2;
+    const int64_t nq = q1 - q0;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= rows * nq) return;
+    const int64_t r = idx / nq, q = q0 + idx % nq;
+    double v[4];
+    theta4<KIND>(seed, (uint32_t)(row0 + r), (uint64_t)q, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t c = 4 * q + j - col0;
+        if (c >= 0 && c < cols) out[r * ldo + c] = scale * v[j];
+    }
+}
+
+// ---- fallback for operands TMA cannot address (odd leading dimension / unaligned base):
+// plain FP64 FMA, one thread per output element, coalesced along n via warp reduction.
+__global__ void gemm_fallback_kernel(const double *__restrict__ u, int64_t ldu, const double *__restrict__ th,
+                                     int64_t ldt, int64_t m, int64_t k, int64_t n, double *__restrict__ y,
+                                     int64_t ldy) {
+    const int64_t o = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= m * k) return;
+    const int64_t row = o / k, col = o % k;
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int64_t j = lane; j < n; j += 32) s = fma(u[row * ldu + j], th[col * ldt + j], s);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) y[row * ldy + col] = s;
+}
+
+static PFN_cuTensorMapEncodeTiled get_encode() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// tensor map over a row-major (rows x cols) FP64 matrix with row stride ld, box [box_rows x 16]
+static int make_map(CUtensorMap *map, const double *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) return fail(RLA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)GK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RLA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return RLA_OK;
+}
+
+static bool tma_ok(const double *p, int64_t ld) {
+    return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 2 == 0);
+}
+
+struct GemmPlan {
+    int wm, wn, bm, bn;
+    int mtiles, ntiles;
+    int64_t kper, nchunks;
+};
+
+static GemmPlan plan_gemm(int64_t m, int64_t k, int64_t n) {
+    GemmPlan p;
+    if (m > 64) { p.wm = 2; p.wn = 4; } else { p.wm = 1; p.wn = 8; }
+    p.bm = p.wm * 64; p.bn = p.wn * 32;
+    p.mtiles = (int)((m + p.bm - 1) / p.bm);
+    p.ntiles = (int)((k + p.bn - 1) / p.bn);
+    const int64_t nk16 = (n + GK - 1) / GK;
+    const int64_t tiles = (int64_t)p.mtiles * p.ntiles;
+    static int waves_env = -1;
+    if (waves_env < 0) { const char *e = getenv("RLA_GEMM_WAVES"); waves_env = e ? atoi(e) : 8; }
+    const int64_t sms = sm_count();
+    const int64_t target = sms * waves_env;
+    // candidates around target / tiles; keep every chunk >= 32 k-blocks unless the problem is
+    // tiny, and pick the chunk count whose grid fills its last wave best (one CTA per SM)
+    const int64_t cmax = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, nk16 / 32), (target + tiles - 1) / tiles));
+    const int64_t cmin = std::max<int64_t>(1, cmax / 2);
+    int64_t chunks = cmax;
+    double best = -1.0;
+    for (int64_t c = cmax; c >= cmin; --c) {
+        const int64_t kper = (nk16 + c - 1) / c;
+        const int64_t nc = (nk16 + kper - 1) / kper;
+        const int64_t grid = nc * tiles;
+        const int64_t waves = (grid + sms - 1) / sms;
+        // useful work / occupied SM time (chunks are kper blocks long, the last may be shorter)
+        const double eff = (double)nk16 * tiles / ((double)waves * sms * kper);
+        if (eff > best + 1e-9) { best = eff; chunks = c; }
+    }
+    p.kper = (nk16 + chunks - 1) / chunks;
+    p.nchunks = (nk16 + p.kper - 1) / p.kper;
+    return p;
+}
+
+template <int WM, int WN, int MODE>
+static int launch_gemm(const CUtensorMap &mu, const CUtensorMap &mt, const GemmArgs &a, int64_t grid, cudaStream_t st) {
+    auto kern = sketch_gemm_kernel<WM, WN, MODE>;
+    constexpr int BM = WM * 64, BN = WN * 32;
+    constexpr int stage = BM * GK * 8 + (MODE == 0 ? BN * GK * 8 : 0);
+    const int smem = GSTAGES * stage + 1024;
+    RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)grid, GTHREADS, smem, st>>>(mu, mt, a);
+    count_launch();
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
+
+// mode 0 explicit / 1 normal / 2 rademacher
+static int sketch_gemm(int mode, const double *theta, int64_t ldt, uint64_t seed, double scale, int64_t row0,
+                       int64_t col0, const double *u, int64_t m, int64_t ldu, int64_t k, int64_t n, double *y,
+                       int64_t ldy, int accumulate, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (m == 0 || k == 0) return RLA_OK;
+    const GemmPlan p = plan_gemm(m, k, n);
+    const size_t need = (size_t)p.nchunks * m * k * sizeof(double);
+    if (ws_bytes < need) return fail(RLA_ERR_WORKSPACE, "sketch gemm: workspace %zu < %zu bytes", ws_bytes, need);
+    CUtensorMap mu, mt;
+    int rc = make_map(&mu, u, m, n, ldu, p.bm);
+    if (rc != RLA_OK) return rc;
+    if (mode == 0) {
+        rc = make_map(&mt, theta, k, n, ldt, p.bn);
+        if (rc != RLA_OK) return rc;
+    } else {
+        mt = mu;
+    }
+    GemmArgs a;
+    a.m = m; a.k = k; a.n = n; a.kper = p.kper; a.nchunks = p.nchunks; a.mtiles = p.mtiles; a.ntiles = p.ntiles;
+    a.ws = static_cast<double *>(ws); a.seed = seed; a.row0 = row0; a.col0 = col0;
+    const int64_t grid = (int64_t)p.mtiles * p.ntiles * p.nchunks;
+    RLA_REQUIRE(grid < (int64_t(1) << 31), "sketch gemm: grid too large");
+    if (p.wm == 2) {
+        rc = mode == 0 ? launch_gemm<2, 4, 0>(mu, mt, a, grid, st)
+           : mode == 1 ? launch_gemm<2, 4, 1>(mu, mt, a, grid, st) : launch_gemm<2, 4, 2>(mu, mt, a, grid, st);
+    } else {
+        rc = mode == 0 ? launch_gemm<1, 8, 0>(mu, mt, a, grid, st)
+           : mode == 1 ? launch_gemm<1, 8, 1>(mu, mt, a, grid, st) : launch_gemm<1, 8, 2>(mu, mt, a, grid, st);
+    }
+    if (rc != RLA_OK) return rc;
+    const int64_t tot = m * k;
+    gemm_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a.ws, p.nchunks, m, k, scale, y, ldy, accumulate);
+    count_launch();
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
+
+}  // namespace rla
+
+using namespace rla;
+
+extern "C" size_t rla_gemm_workspace_bytes(int64_t m, int64_t k, int64_t n) {
+    if (m <= 0 || k <= 0 || n <= 0) return 0;
+    const GemmPlan p = plan_gemm(m, k, n);
+    return (size_t)p.nchunks * m * k * sizeof(double);
+}
+
+extern "C" int rla_gauss_apply_explicit_f64(const double *theta, int64_t k, int64_t n, int64_t ldt, const double *u,
+                                            int64_t m, int64_t ldu, double *y, int64_t ldy, void *ws,
+                                            size_t ws_bytes, void *stream) {
+    RLA_REQUIRE(k >= 0 && n >= 1 && m >= 0 && ldt >= n && ldu >= n && ldy >= k, "rla_gauss_apply_explicit_f64: bad sizes");
+    if (m == 0 || k == 0) return RLA_OK;
+    RLA_REQUIRE(theta && u && y, "rla_gauss_apply_explicit_f64: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!tma_ok(theta, ldt) || !tma_ok(u, ldu)) {
+        const int64_t outs = m * k;
+        gemm_fallback_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, st>>>(u, ldu, theta, ldt, m, k, n, y, ldy);
+        count_launch();
+        RLA_CUDA_CHECK(cudaGetLastError());
+        return RLA_OK;
+    }
+    RLA_REQUIRE(ws, "rla_gauss_apply_explicit_f64: null workspace");
+    return sketch_gemm(0, theta, ldt, 0, 1.0, 0, 0, u, m, ldu, k, n, y, ldy, 0, ws, ws_bytes, st);
+}
+
+extern "C" int rla_embed_apply_rng_f64(uint64_t seed, int kind, double scale, int64_t row0, int64_t k_blk,
+                                       int64_t col0, int64_t n, const double *u, int64_t m, int64_t ldu, double *y,
+                                       int64_t ldy, int accumulate, void *ws, size_t ws_bytes, void *stream) {
+    RLA_REQUIRE(kind == 0 || kind == 1, "rla_embed_apply_rng_f64: kind must be 0 (normal) or 1 (rademacher)");
+    RLA_REQUIRE(k_blk >= 0 && n >= 1 && m >= 0 && ldu >= n && ldy >= k_blk && row0 >= 0 && col0 >= 0,
+                "rla_embed_apply_rng_f64: bad sizes");
+    RLA_REQUIRE(col0 % 16 == 0, "rla_embed_apply_rng_f64: col0 must be a multiple of 16");
+    RLA_REQUIRE(row0 + k_blk <= (int64_t(1) << 32), "rla_embed_apply_rng_f64: more than 2^32 sketch rows");
+    if (m == 0 || k_blk == 0) return RLA_OK;
+    RLA_REQUIRE(u && y && ws, "rla_embed_apply_rng_f64: null pointer");
+    RLA_REQUIRE(tma_ok(u, ldu), "rla_embed_apply_rng_f64: u must be 16-byte aligned with an even leading dimension");
+    return sketch_gemm(kind == 0 ? 1 : 2, nullptr, 0, seed, scale, row0, col0, u, m, ldu, k_blk, n, y, ldy,
+                       accumulate, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int rla_theta_materialize_f64(uint64_t seed, int kind, double scale, int64_t row0, int64_t rows,
+                                         int64_t col0, int64_t cols, double *out, int64_t ldo, void *stream) {
+    RLA_REQUIRE(kind == 0 || kind == 1, "rla_theta_materialize_f64: kind must be 0 or 1");
+    RLA_REQUIRE(rows >= 0 && cols >= 0 && row0 >= 0 && col0 >= 0 && ldo >= cols, "rla_theta_materialize_f64: bad sizes");
+    if (rows == 0 || cols == 0) return RLA_OK;
+    RLA_REQUIRE(out, "rla_theta_materialize_f64: null pointer");
+    const int64_t nq = ((col0 + cols + 3) >> 2) - (col0 >> 2);
+    const int64_t tot = rows * nq;
+    const unsigned grid = (unsigned)((tot + 255) / 256);
+    if (kind == 0) theta_materialize_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, scale, row0, rows, col0, cols, out, ldo);
+    else theta_materialize_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, scale, row0, rows, col0, cols, out, ldo);
+    count_launch();
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}

@@ -1,0 +1,72 @@
+// rng.cuh -- counter-based generator of the virtual embedding matrix Theta.
+//
+// Theta[row, col] (row = sketch index, col = index in the vector dimension) is a pure
+// function of (seed, kind, row, col): Philox4x32-10 keyed by the 64-bit seed, counter
+// (col / 4, row, col / 2^34, kind), whose four 32-bit outputs become the four entries
+// Theta[row, 4q .. 4q+3].  The GEMM kernel (gemm.cu) generates exactly the entries its
+// DMMA fragments need, in registers; rla_theta_materialize_f64 exports the same values
+// (same device function, hence bit-identical) for parity checks against the oracle.
+//
+//   kind 0: standard normal by Box-Muller in FP32 (MUFU lg2 / sin / cos), widened to FP64
+//   kind 1: Rademacher +-1 (one bit per entry)
+// The 1/sqrt(k) scale of the reference (rla/embeddings.py:269) is applied by the caller.
+#pragma once
+#include <stdint.h>
+
+namespace rla {
+
+struct PhiloxOut { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ PhiloxOut philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                            uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = mulhi32(M0, c0), l0 = M0 * c0;
+        const uint32_t h1 = mulhi32(M1, c2), l1 = M1 * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += W0; k1 += W1;
+    }
+    return PhiloxOut{c0, c1, c2, c3};
+}
+
+// two standard normals from two 32-bit words (FP32 Box-Muller); deterministic on sm_100
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1) {
+    const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (a + 0.5) 2^-32, > 0
+    const float ang = (float)(int32_t)b * 1.4629180792671596e-9f;                         // pi 2^-31 b, [-pi, pi)
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));                            // sqrt(-2 ln u1)
+    n0 = r * __cosf(ang);
+    n1 = r * __sinf(ang);
+}
+
+// the four entries Theta[row, 4*q .. 4*q+3]  (q = col / 4) as doubles, unscaled
+template <int KIND>
+__device__ __forceinline__ void theta4(uint64_t seed, uint32_t row, uint64_t q, double (&out)[4]) {
+    if (KIND == 0) {
+        const PhiloxOut p = philox4x32_10((uint32_t)q, row, (uint32_t)(q >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        float n0, n1, n2, n3;
+        box_muller(p.x, p.y, n0, n1);
+        box_muller(p.z, p.w, n2, n3);
+        out[0] = (double)n0; out[1] = (double)n1; out[2] = (double)n2; out[3] = (double)n3;
+    } else {
+        // 128 sign bits per Philox block: block index q / 32, bits 4*(q%32) .. +3
+        const uint64_t blk = q >> 5;
+        const PhiloxOut p = philox4x32_10((uint32_t)blk, row, (uint32_t)(blk >> 32), 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint32_t sel = (uint32_t)(q & 31);
+        const uint32_t wsel = sel >> 3;
+        const uint32_t word = wsel == 0 ? p.x : (wsel == 1 ? p.y : (wsel == 2 ? p.z : p.w));
+        const uint32_t bits = word >> (4 * (sel & 7));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = ((bits >> j) & 1u) ? -1.0 : 1.0;
+    }
+}
+
+}  // namespace rla

@@ -4,14 +4,8 @@
 #define RLA_STUB(name) return ::rla::fail(RLA_ERR_UNSUPPORTED, name ": not implemented yet")
 
 extern "C" {
-size_t rla_gemm_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-int rla_gauss_apply_explicit_f64(const double *, int64_t, int64_t, int64_t, const double *, int64_t, int64_t,
-                                 double *, int64_t, void *, size_t, void *) { RLA_STUB("rla_gauss_apply_explicit_f64"); }
-int rla_embed_apply_rng_f64(uint64_t, int, double, int64_t, int64_t, int64_t, int64_t, const double *, int64_t, int64_t,
-                            double *, int64_t, int, void *, size_t, void *) { RLA_STUB("rla_embed_apply_rng_f64"); }
 int rla_embed_apply_rng_f32(uint64_t, int, float, int64_t, int64_t, int64_t, int64_t, const float *, int64_t, int64_t,
                             float *, int64_t, int, void *, size_t, void *) { RLA_STUB("rla_embed_apply_rng_f32"); }
-int rla_theta_materialize_f64(uint64_t, int, double, int64_t, int64_t, int64_t, int64_t, double *, int64_t, void *) { RLA_STUB("rla_theta_materialize_f64"); }
 int rla_gemm_nn_f64(const double *, int64_t, int64_t, int64_t, const double *, int64_t, int64_t, double *, int64_t, void *) { RLA_STUB("rla_gemm_nn_f64"); }
 int rla_spmm_csr_f64(const int64_t *, const int32_t *, const double *, int64_t, int64_t, const double *, int64_t, int64_t,
                      double *, int64_t, void *) { RLA_STUB("rla_spmm_csr_f64"); }
