@@ -30,7 +30,8 @@ namespace rla {
 constexpr int GK = 16;                 // doubles per row per stage (128 bytes = swizzle span)
 constexpr int GSTAGES = 4;
 constexpr int GWARPS = 8;
-constexpr int GTHREADS = GWARPS * 32;
+constexpr int GTHREADS = GWARPS * 32;   // consumer threads
+constexpr int GPRODUCERS = 128;           // producer threads (one warpgroup)
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,21 +80,33 @@ struct GemmArgs {
     int64_t row0, col0;       // offsets of this block inside the virtual Theta
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // MODE 0: Theta explicit (second tensor map); 1: Philox normal; 2: Philox Rademacher
+//
+// Warp roles: warps 0..7 are DMMA consumers (2 per SM sub-partition, free-running: they
+// only meet through the per-stage full/empty mbarriers, so one warp's shared-memory
+// bubble is covered by the other's DMMAs); warps 8..11 are producers: lane 0 of warp 8
+// issues the TMA loads, and in the RNG modes all 128 producer threads generate the
+// [BN x 16] Theta tile of the stage (one sketch row each, four Philox blocks) straight
+// into the swizzled shared-memory layout the consumers read.
 template <int WM, int WN, int MODE>
-__global__ void __launch_bounds__(GTHREADS, 1)
+__global__ void __launch_bounds__(GTHREADS + GPRODUCERS, 1)
 sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT, const GemmArgs a) {
     constexpr int BM = WM * 64, BN = WN * 32;
-    static_assert(WM * WN == GWARPS, "8 warps");
+    static_assert(WM * WN == GWARPS, "8 consumer warps");
     constexpr int A_BYTES = BM * GK * 8;
-    constexpr int B_BYTES = (MODE == 0) ? BN * GK * 8 : 0;
+    constexpr int B_BYTES = BN * GK * 8;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TX_BYTES = (MODE == 0) ? STAGE_BYTES : A_BYTES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[GSTAGES];
+    __shared__ __align__(8) uint64_t empty_bar[GSTAGES];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int wm = warp / WN, wn = warp % WN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // blockIdx.x = ntile + ntiles * (mtile + mtiles * chunk): CTAs sharing a U chunk are adjacent
     int64_t b = blockIdx.x;
     const int ntile = (int)(b % a.ntiles); b /= a.ntiles;
@@ -107,82 +120,103 @@ sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < GSTAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < GSTAGES; ++s) {
+            mbar_init(&full_bar[s], MODE == 0 ? 1 : 1 + GPRODUCERS / 32);
+            mbar_init(&empty_bar[s], GWARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int it) {   // thread 0 only
-        const int s = it % GSTAGES;
-        unsigned char *st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int x = (int)((kb0 + it) * GK);
-        tma_load_2d(st, &mapU, &full_bar[s], x, m0);
-        if (MODE == 0) tma_load_2d(st + A_BYTES, &mapT, &full_bar[s], x, n0);
-    };
-    if (tid == 0) {
-        for (int it = 0; it < GSTAGES - 1 && it < iters; ++it) issue(it);
+    if (warp >= GWARPS) {
+        // ------------------------------------------------------------ producers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int p = tid - GTHREADS;                  // 0..127: row of the Theta tile
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % GSTAGES;
+            if (it >= GSTAGES) mbar_wait(&empty_bar[s], ((it / GSTAGES) - 1) & 1);
+            unsigned char *st = smem + s * STAGE_BYTES;
+            if (p == 0) {
+                mbar_expect_tx(&full_bar[s], TX_BYTES);
+                const int x = (int)((kb0 + it) * GK);
+                tma_load_2d(st, &mapU, &full_bar[s], x, m0);
+                if (MODE == 0) tma_load_2d(st + A_BYTES, &mapT, &full_bar[s], x, n0);
+            }
+            if (MODE != 0) {
+#pragma unroll 1
+                for (int r = p; r < BN; r += GPRODUCERS) {
+                    if (n0 + r < a.k) {
+                        const uint32_t trow = (uint32_t)(a.row0 + n0 + r);
+                        const uint64_t q0 = (uint64_t)(a.col0 + (kb0 + it) * GK) >> 2;
+                        unsigned char *rowp = st + A_BYTES + r * 128;
+                        const int sw = r & 7;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            double v[4];
+                            if (MODE == 1) theta4<0>(a.seed, trow, q0 + c, v);
+                            else theta4<1>(a.seed, trow, q0 + c, v);
+                            *reinterpret_cast<double2 *>(rowp + (((2 * c) ^ sw) << 4)) = make_double2(v[0], v[1]);
+                            *reinterpret_cast<double2 *>(rowp + (((2 * c + 1) ^ sw) << 4)) = make_double2(v[2], v[3]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[s]);
+            }
+        }
+        return;
     }
 
+    // ---------------------------------------------------------------- consumers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    // columns of the sketch (rows of Theta) owned by this thread's B fragments
-    const int ncol_base = n0 + wn * 32 + g;
-    // number of 8-wide column groups of this warp that fall inside the sketch (ragged k)
+    // 8-wide column groups of this warp that fall inside the sketch (ragged k), row groups inside m
     const int64_t ng64 = (a.k - (n0 + wn * 32) + 7) / 8;
     const int ngroups = ng64 < 0 ? 0 : (ng64 > 4 ? 4 : (int)ng64);
-    // rows groups inside m
     const int64_t mg64 = (a.m - (m0 + wm * 64) + 7) / 8;
     const int mgroups = mg64 < 0 ? 0 : (mg64 > 8 ? 8 : (int)mg64);
 
     for (int it = 0; it < iters; ++it) {
         const int s = it % GSTAGES;
-        // slot (it-1) % S was released by the barrier at the end of the previous iteration
-        if (tid == 0 && it + GSTAGES - 1 < iters) issue(it + GSTAGES - 1);
-        // B fragments for this k block
-        double bf[4][4];
-        if (MODE != 0) {
-            const uint64_t q = (uint64_t)(a.col0 + (kb0 + it) * GK + 4 * t) >> 2;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < ngroups) {
-                    if (MODE == 1) theta4<0>(a.seed, (uint32_t)(a.row0 + ncol_base + 8 * j), q, bf[j]);
-                    else theta4<1>(a.seed, (uint32_t)(a.row0 + ncol_base + 8 * j), q, bf[j]);
-                }
-            }
-        }
         mbar_wait(&full_bar[s], (it / GSTAGES) & 1);
         const double *At = reinterpret_cast<const double *>(smem + s * STAGE_BYTES) + (wm * 64) * GK;
-        if (MODE == 0) {
-            const double *Bt = reinterpret_cast<const double *>(smem + s * STAGE_BYTES + A_BYTES) + (wn * 32) * GK;
+        const double *Bt = reinterpret_cast<const double *>(smem + s * STAGE_BYTES + A_BYTES) + (wn * 32) * GK;
+        double bf[4][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) lds_row4(Bt, 8 * j + g, t, bf[j]);
-        }
+        for (int j = 0; j < 4; ++j) lds_row4(Bt, 8 * j + g, t, bf[j]);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             double af[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) lds_row4(At, 8 * (4 * half + i) + g, t, af[i]);
+            if (half == 1) {
+                // all shared-memory reads of this stage are issued: release the slot
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+            }
+            // kk outermost: consecutive DMMAs never hit the same accumulator
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (4 * half + i < mgroups) {
+            for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (j < ngroups) {
+                for (int i = 0; i < 4; ++i) {
+                    if (4 * half + i < mgroups) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
+                        for (int j = 0; j < 4; ++j) {
+                            if (j < ngroups)
                                 dmma884(acc[4 * half + i][j][0], acc[4 * half + i][j][1], af[i][kk], bf[j][kk]);
                         }
                     }
                 }
             }
         }
-        __syncthreads();   // everyone is done with slot s; it is refilled next iteration
     }
 
     // partial tile -> workspace [chunk][m][k]
@@ -319,10 +353,10 @@ template <int WM, int WN, int MODE>
 static int launch_gemm(const CUtensorMap &mu, const CUtensorMap &mt, const GemmArgs &a, int64_t grid, cudaStream_t st) {
     auto kern = sketch_gemm_kernel<WM, WN, MODE>;
     constexpr int BM = WM * 64, BN = WN * 32;
-    constexpr int stage = BM * GK * 8 + (MODE == 0 ? BN * GK * 8 : 0);
+    constexpr int stage = BM * GK * 8 + BN * GK * 8;
     const int smem = GSTAGES * stage + 1024;
     RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(unsigned)grid, GTHREADS, smem, st>>>(mu, mt, a);
+    kern<<<(unsigned)grid, GTHREADS + GPRODUCERS, smem, st>>>(mu, mt, a);
     count_launch();
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;
