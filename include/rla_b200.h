@@ -138,12 +138,6 @@ int rla_embed_apply_rng_f64(uint64_t seed, int kind, double scale,
                             const double *u_dev, int64_t m, int64_t ldu,
                             double *y_dev, int64_t ldy, int accumulate,
                             void *ws_dev, size_t ws_bytes, void *stream);
-int rla_embed_apply_rng_f32(uint64_t seed, int kind, float scale,
-                            int64_t row0, int64_t k_blk, int64_t col0, int64_t n,
-                            const float *u_dev, int64_t m, int64_t ldu,
-                            float *y_dev, int64_t ldy, int accumulate,
-                            void *ws_dev, size_t ws_bytes, void *stream);
-
 /* Export what the on-the-fly generator produces (parity tooling; replaces
  * get_random_matrix / _get_random_block, rla/embeddings.py:87-100, 452-461). */
 int rla_theta_materialize_f64(uint64_t seed, int kind, double scale,
@@ -152,10 +146,12 @@ int rla_theta_materialize_f64(uint64_t seed, int kind, double scale,
 
 /* out(m, n) = V(m, k) * Theta(k, n): the adjoint / explicit-matrix product
  * (SrhtEmbedding.apply_adjoint rla/embeddings.py:175-178, rb.lincomb(T.T)
- * mor/sketched_reductor.py:99-100). */
+ * mor/sketched_reductor.py:99-100).  Theta is transposed into scratch and the product
+ * runs on the same tensor-core kernel as the sketch. */
+size_t rla_gemm_nn_workspace_bytes(int64_t m, int64_t k, int64_t n);
 int rla_gemm_nn_f64(const double *v_dev, int64_t m, int64_t k, int64_t ldv,
                     const double *theta_dev, int64_t n, int64_t ldt,
-                    double *out_dev, int64_t ldo, void *stream);
+                    double *out_dev, int64_t ldo, void *ws_dev, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------ sketched reductor ops ----
  * CSR SpMM in the reference's row layout: out[c, i] = sum_j A[i, j] * u[c, j]
@@ -174,11 +170,16 @@ int rla_gram_schmidt_f64(double *a_dev, int64_t r, int64_t k, int64_t lda, int64
                          double *R_dev, int32_t *flags_dev,
                          double atol, double rtol, double reiteration_threshold, void *stream);
 
-/* Singular values / one-sided Jacobi SVD of a small k x m sketch (m <= k):
- * A (k, m) row-major is overwritten by U * diag(s); s_dev gets the m singular
- * values (unsorted); V_dev (m x m, may be NULL) the right vectors. */
+/* One-sided Jacobi (Hestenes) SVD of a k x m sketch held in the row layout: a_dev is
+ * (m, k), row p = column p of the k x m matrix.  On return the rows are u_p * s_p
+ * (mutually orthogonal), s_dev holds the m singular values (unsorted) and V_dev (m x m,
+ * row p = p-th right singular vector; may be NULL) the accumulated rotations.
+ * pairs_dev: round-robin schedule, (me - 1) rounds x (me / 2) int32 pairs with
+ * me = m rounded up to even, -1 marking the bye; rot_dev: one int32 of scratch.
+ * Synchronises the stream once per sweep to test convergence. */
 int rla_svd_jacobi_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
-                       double *s_dev, double *V_dev, int max_sweeps, void *stream);
+                       double *s_dev, double *V_dev, const int32_t *pairs_dev, int32_t *rot_dev,
+                       int max_sweeps, double tol, int *sweeps_done, void *stream);
 
 /* Sketched residual norm  || sum_q th[q] S_q a - sum_p tr[p] b_p ||_2
  * (ResidualErrorEstimator.estimate_error, mor/sketched_reductor.py:216-219);

@@ -41,13 +41,13 @@ _SIGS = {
                                              _vp, c_size_t, _vp]),
     "rla_embed_apply_rng_f64": (c_int, [c_uint64, c_int, c_double, c_int64, c_int64, c_int64, c_int64, _vp, c_int64,
                                         c_int64, _vp, c_int64, c_int, _vp, c_size_t, _vp]),
-    "rla_embed_apply_rng_f32": (c_int, [c_uint64, c_int, c_float, c_int64, c_int64, c_int64, c_int64, _vp, c_int64,
-                                        c_int64, _vp, c_int64, c_int, _vp, c_size_t, _vp]),
     "rla_theta_materialize_f64": (c_int, [c_uint64, c_int, c_double, c_int64, c_int64, c_int64, c_int64, _vp, c_int64, _vp]),
-    "rla_gemm_nn_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, c_int64, c_int64, _vp, c_int64, _vp]),
+    "rla_gemm_nn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rla_gemm_nn_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, c_int64, c_int64, _vp, c_int64, _vp, c_size_t, _vp]),
     "rla_spmm_csr_f64": (c_int, [_vp, _vp, _vp, c_int64, c_int64, _vp, c_int64, c_int64, _vp, c_int64, _vp]),
     "rla_gram_schmidt_f64": (c_int, [_vp, c_int64, c_int64, c_int64, c_int64, _vp, _vp, c_double, c_double, c_double, _vp]),
-    "rla_svd_jacobi_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, c_int, _vp]),
+    "rla_svd_jacobi_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, _vp, c_int, c_double,
+                                   POINTER(c_int), _vp]),
     "rla_residual_norm_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int64, _vp, _vp, _vp]),
 }
 

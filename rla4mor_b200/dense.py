@@ -50,7 +50,7 @@ def _tma_friendly(x):
 
 def gauss_apply_explicit(theta, u, out=None):
     """(m, n) x (k, n)^T -> (m, k), float64."""
-    theta, u = _rows(theta), _rows(u)
+    theta, u = _tma_friendly(_rows(theta)), _tma_friendly(_rows(u))
     assert theta.dtype == torch.float64 and u.dtype == torch.float64
     k, n = theta.shape
     m = u.shape[0]

@@ -1,0 +1,141 @@
+"""Device wrappers for the small operations around the sketch (csrc/reductor.cu):
+CSR SpMM, V @ Theta, Gram matrices, Gram-Schmidt of the sketched basis, Jacobi SVD of a
+k x m sketch and the sketched residual norm.  CUDA tensors in, CUDA tensors out."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import dense
+from ._lib import check, lib, stream_ptr
+
+
+def _rows(x):
+    return dense._rows(x)
+
+
+def spmm_csr(rowptr, col, val, shape, u):
+    """out[c, i] = sum_j A[i, j] u[c, j]  (A_q.apply(U), mor/sketched_reductor.py:69-70)."""
+    u = _rows(u).to(torch.float64)
+    n_rows, n_cols = shape
+    assert u.shape[1] == n_cols
+    m = u.shape[0]
+    out = torch.empty((m, n_rows), dtype=torch.float64, device=u.device)
+    if m == 0 or n_rows == 0:
+        return out
+    with torch.cuda.device(u.device):
+        check(lib().rla_spmm_csr_f64(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), n_rows, n_cols,
+                                     u.data_ptr(), m, dense._ld(u), out.data_ptr(), out.stride(0), stream_ptr()),
+              "rla_spmm_csr_f64")
+    return out
+
+
+def gemm_nn(v, theta):
+    """(m, k) @ (k, n) -> (m, n): adjoint / basis update (mor/sketched_reductor.py:99-100)."""
+    v, theta = _rows(v).to(torch.float64), _rows(theta).to(torch.float64)
+    m, k = v.shape
+    assert theta.shape[0] == k
+    n = theta.shape[1]
+    out = torch.empty((m, n), dtype=torch.float64, device=v.device)
+    if m == 0 or n == 0:
+        return out
+    if k == 0:
+        return out.zero_()
+    v = dense._tma_friendly(v)
+    with torch.cuda.device(v.device):
+        ws = dense._workspace(lib().rla_gemm_nn_workspace_bytes(m, k, n), v.device)
+        check(lib().rla_gemm_nn_f64(v.data_ptr(), m, k, dense._ld(v), theta.data_ptr(), n, dense._ld(theta),
+                                    out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(), stream_ptr()),
+              "rla_gemm_nn_f64")
+    return out
+
+
+def gram(a, b):
+    """G[i, j] = <a_i, b_j> for row blocks a (r, k), b (q, k): the reduced Galerkin
+    matrices (Theta U)^H (Theta R^-1 A_q U) of mor/sketched_reductor.py:161-162."""
+    return dense.gauss_apply_explicit(dense._tma_friendly(_rows(b).to(torch.float64)),
+                                      dense._tma_friendly(_rows(a).to(torch.float64)))
+
+
+def gram_schmidt(A, offset=0, atol=1e-13, rtol=1e-13, reiteration_threshold=9e-1):
+    """pyMOR-style gram_schmidt(A, offset=offset, return_R=True) on the rows of A
+    (mor/sketched_reductor.py:94).  Returns (Q, R) with dependent rows removed."""
+    A = _rows(A).to(torch.float64).clone()
+    r, k = A.shape
+    R = torch.empty((r, r), dtype=torch.float64, device=A.device)
+    flags = torch.empty((max(r, 1),), dtype=torch.int32, device=A.device)
+    if r == 0:
+        return A, R
+    with torch.cuda.device(A.device):
+        check(lib().rla_gram_schmidt_f64(A.data_ptr(), r, k, A.stride(0), int(offset), R.data_ptr(), flags.data_ptr(),
+                                         float(atol), float(rtol), float(reiteration_threshold), stream_ptr()),
+              "rla_gram_schmidt_f64")
+    keep = flags[:r] == 0
+    if not bool(keep.all()):
+        A, R = A[keep], R[keep]
+    return A, R
+
+
+def _round_robin(m):
+    me = m + (m & 1)
+    players = list(range(me))
+    rounds = []
+    for _ in range(me - 1):
+        pairs = []
+        for i in range(me // 2):
+            p, q = players[i], players[me - 1 - i]
+            if p >= m or q >= m:
+                p, q = -1, -1
+            pairs.append((p, q))
+        rounds.append(pairs)
+        players = [players[0]] + [players[-1]] + players[1:-1]
+    return np.asarray(rounds, dtype=np.int32).reshape(-1)
+
+
+_PAIRS = {}
+
+
+def svd_jacobi(S, want_v=False, max_sweeps=30, tol=1e-15):
+    """One-sided Jacobi SVD of the k x m sketch held as a row block S (m, k).
+    Returns (U_rows (m, k) orthonormal rows, s (m,), V (m, m) or None), singular values
+    sorted descending: S = (V^T diag(s) U_rows) in the row layout, i.e. the k x m matrix
+    S^T = U_rows^T diag(s) V."""
+    A = _rows(S).to(torch.float64).clone()
+    m, k = A.shape
+    s = torch.empty((m,), dtype=torch.float64, device=A.device)
+    V = torch.empty((m, m), dtype=torch.float64, device=A.device) if want_v else None
+    key = (m, A.device.index)
+    if key not in _PAIRS:
+        _PAIRS[key] = torch.from_numpy(_round_robin(m)).to(A.device)
+    rot = torch.zeros((1,), dtype=torch.int32, device=A.device)
+    done = ctypes.c_int(0)
+    with torch.cuda.device(A.device):
+        check(lib().rla_svd_jacobi_f64(A.data_ptr(), k, m, A.stride(0), s.data_ptr(),
+                                       V.data_ptr() if want_v else None, _PAIRS[key].data_ptr(), rot.data_ptr(),
+                                       int(max_sweeps), float(tol), ctypes.byref(done), stream_ptr()),
+              "rla_svd_jacobi_f64")
+    order = torch.argsort(s, descending=True)
+    s = s[order]
+    A = A[order]
+    U_rows = A / torch.clamp(s, min=torch.finfo(torch.float64).tiny).unsqueeze(1)
+    return U_rows, s, (V[order] if want_v else None)
+
+
+def residual_norm(S_terms, theta_lhs, b_terms, theta_rhs, a):
+    """|| sum_q th_q S_q a - sum_p tr_p b_p ||_2 (mor/sketched_reductor.py:216-219).
+    S_terms: list of (k, r) CUDA tensors; b_terms: list of (k,) tensors."""
+    dev = a.device if isinstance(a, torch.Tensor) else torch.device("cuda", torch.cuda.current_device())
+    Q = len(S_terms)
+    S = torch.stack([t.to(torch.float64).contiguous() for t in S_terms]) if Q else torch.empty((0, 1, 0), dtype=torch.float64, device=dev)
+    k = S.shape[1] if Q else (b_terms[0].numel() if b_terms else 1)
+    r = S.shape[2] if Q else 0
+    P = len(b_terms)
+    b = torch.stack([t.to(torch.float64).reshape(-1) for t in b_terms]) if P else torch.empty((0, k), dtype=torch.float64, device=dev)
+    th = torch.as_tensor(np.asarray(theta_lhs, dtype=np.float64), device=dev)
+    tr = torch.as_tensor(np.asarray(theta_rhs, dtype=np.float64), device=dev)
+    av = torch.as_tensor(a, dtype=torch.float64, device=dev).reshape(-1).contiguous()
+    out = torch.empty((1,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().rla_residual_norm_f64(S.data_ptr(), Q, k, r, th.data_ptr(), av.data_ptr(), b.data_ptr(), P,
+                                          tr.data_ptr(), out.data_ptr(), stream_ptr()), "rla_residual_norm_f64")
+    return out

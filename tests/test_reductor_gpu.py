@@ -1,0 +1,143 @@
+"""GPU parity of the sketched-reductor operations against the oracle's restatement of
+mor/sketched_reductor.py."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import embeddings_oracle as eo
+from oracle import reductor_oracle as ro
+from golden_util import rel_fro
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import rla4mor_b200
+    rla4mor_b200.lib()
+    return rla4mor_b200
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _fem_terms(nx, Q=4, seed=0):
+    """Q block-wise 5-point stiffness-like SPD terms on an nx x nx grid (thermal-block style)."""
+    n = nx * nx
+    ex = np.ones(nx)
+    T = sp.diags([-ex[:-1], 2 * ex, -ex[:-1]], [-1, 0, 1])
+    L = (sp.kron(sp.eye(nx), T) + sp.kron(T, sp.eye(nx))).tocsr()
+    idx = np.arange(n)
+    blk = (idx // nx >= nx // 2) * 2 + (idx % nx >= nx // 2)
+    terms = []
+    for q in range(Q):
+        D = sp.diags((blk == q % 4).astype(float) + 0.01)
+        terms.append((D @ L @ D + 1e-3 * sp.eye(n)).tocsr())
+    return terms, n
+
+
+def test_spmm_and_gemm_nn_and_gram(rb):
+    from rla4mor_b200 import reductor_ops as ops
+    A = sp.random(3000, 2500, density=3e-3, random_state=1, format="csr")
+    u = np.random.RandomState(0).standard_normal((11, 2500))
+    op = rb.MatrixOperator(A)
+    got = op.apply(op.source.from_numpy(u)).to_numpy()
+    assert rel_fro(got, np.asarray((A @ u.T).T)) < 1e-13
+    w = np.random.RandomState(1).standard_normal((4, 3000))
+    assert rel_fro(op.apply_adjoint(op.range.from_numpy(w)).to_numpy(), np.asarray((A.T @ w.T).T)) < 1e-13
+    v = np.random.RandomState(2).standard_normal((7, 33))
+    th = np.random.RandomState(3).standard_normal((33, 5001))
+    assert rel_fro(ops.gemm_nn(_dev(v), _dev(th)).cpu().numpy(), v @ th) < 1e-12
+    a = np.random.RandomState(4).standard_normal((9, 1000))
+    b = np.random.RandomState(5).standard_normal((13, 1000))
+    assert rel_fro(ops.gram(_dev(a), _dev(b)).cpu().numpy(), a @ b.T) < 1e-12
+
+
+@pytest.mark.parametrize("r,k", [(6, 40), (20, 1000), (64, 4000), (3, 5000)])
+def test_gram_schmidt_matches_oracle(rb, r, k):
+    from rla4mor_b200 import reductor_ops as ops
+    A = np.random.RandomState(r).standard_normal((r, k))
+    A[r // 2] = A[0] * 0.999 + 1e-3 * A[r // 2]                 # nearly dependent: triggers re-iteration
+    Qd, Rd = ops.gram_schmidt(_dev(A))
+    Qo, Ro = ro.gram_schmidt(A)
+    assert rel_fro(Qd.cpu().numpy(), Qo) < 1e-10 and rel_fro(Rd.cpu().numpy(), Ro) < 1e-12
+    assert rel_fro((Qd @ Qd.T).cpu().numpy(), np.eye(Qd.shape[0])) < 1e-13
+    # offset and removal of a dependent row
+    A2 = np.vstack([Qo[:3], A[3:5], Qo[0] + Qo[1]])
+    Q2, R2 = ops.gram_schmidt(_dev(A2), offset=3)
+    Qo2, Ro2 = ro.gram_schmidt(A2, offset=3)
+    assert Q2.shape == Qo2.shape and R2.shape == Ro2.shape
+    assert rel_fro(Q2.cpu().numpy(), Qo2) < 1e-10 and rel_fro(R2.cpu().numpy(), Ro2) < 1e-10
+
+
+@pytest.mark.parametrize("m,k", [(5, 40), (32, 600), (64, 1024), (33, 500)])
+def test_jacobi_svd(rb, m, k):
+    from rla4mor_b200 import reductor_ops as ops
+    S = np.random.RandomState(m).standard_normal((m, k)) * np.logspace(0, -6, m)[:, None]
+    U, s, V = ops.svd_jacobi(_dev(S), want_v=True)
+    s_ref = np.linalg.svd(S, compute_uv=False)
+    assert np.max(np.abs(s.cpu().numpy() - s_ref) / s_ref[0]) < 1e-13
+    rec = (V.T * s) @ U                                          # S = V^T diag(s) U_rows
+    assert rel_fro(rec.cpu().numpy(), S) < 1e-12
+    assert rel_fro((U @ U.T).cpu().numpy(), np.eye(m)) < 1e-10
+
+
+def test_residual_norm(rb):
+    from rla4mor_b200 import reductor_ops as ops
+    rs = np.random.RandomState(0)
+    S = [rs.standard_normal((300, 12)) for _ in range(3)]
+    b = [rs.standard_normal(300) for _ in range(2)]
+    a = rs.standard_normal(12)
+    got = float(ops.residual_norm([_dev(x) for x in S], [0.5, -1.0, 2.0], [_dev(x) for x in b], [1.0, 0.3], _dev(a)).cpu())
+    ref = ro.residual_norm(S, [0.5, -1.0, 2.0], [x.reshape(-1, 1) for x in b], [1.0, 0.3], a)
+    assert abs(got - ref) / ref < 1e-13
+
+
+@pytest.mark.parametrize("kind", ["srht", "gauss"])
+def test_sketched_reductor_pipeline(rb, kind):
+    terms, n = _fem_terms(48)
+    rs = np.random.RandomState(3)
+    f = [rs.standard_normal(n)]
+    k = 200
+    space = rb.DeviceVectorSpace(n, id="STATE")
+    ops_dev = [rb.MatrixOperator(A, source_id="STATE", range_id="STATE") for A in terms]
+    if kind == "srht":
+        emb = rb.SrhtEmbedding(source=space, options={"range_dim": k}, _seed=1)
+        theta_apply = lambda V: eo.srht_apply(V, k, 1)
+    else:
+        emb = rb.GaussianEmbedding(source=space, options={"range_dim": k}, _seed=1)
+        theta = eo.gaussian_random_matrix(k, n, 1)
+        theta_apply = lambda V: eo.gaussian_apply(V, theta)
+    red = rb.SketchedReductor(ops_dev, f, emb)
+    U1, U2 = rs.standard_normal((5, n)), rs.standard_normal((4, n))
+    # oracle side: same sequence of operations (reductor_oracle.py)
+    srb = np.zeros((0, k)); S = [np.zeros((k, 0)) for _ in terms]; rbo = np.zeros((0, n))
+    for U in (U1, U2):
+        red.extend_basis(U)
+        off = srb.shape[0]
+        srb = np.vstack([srb, theta_apply(U)]); rbo = np.vstack([rbo, U])
+        new = ro.sketch_affine_terms(theta_apply, terms, U)
+        S = [np.hstack([s0, s1]) for s0, s1 in zip(S, new)]
+        srb, R, T, S = ro.orthonormalize_sketch(srb, S, offset=off)
+        rbo = ro.update_basis(rbo, T)
+    srhs = [theta_apply(f[0].reshape(1, -1)).reshape(-1, 1)]
+    assert rel_fro(red.srb.cpu().numpy(), srb) < 1e-9
+    assert rel_fro(red.rb.cpu().numpy(), rbo) < 1e-9
+    for got, ref in zip(red.sketched_operator_matrices(), S):
+        assert rel_fro(got.cpu().numpy(), ref) < 1e-9
+    rom = red.reduce()
+    lhs, rhs = ro.galerkin_system(srb, S, srhs)
+    for got, ref in zip(rom.lhs, lhs):
+        assert rel_fro(got.cpu().numpy(), ref) < 1e-9
+    assert rel_fro(rom.rhs[0].cpu().numpy(), rhs[0][:, 0]) < 1e-9
+    th = [1.0, 0.5, 2.0, 0.1]
+    a = rom.solve(th, [1.0])
+    err = rom.estimate_error(a, th, [1.0])
+    ref_err = ro.residual_norm(S, th, srhs, [1.0], a.cpu().numpy())
+    assert abs(err - ref_err) / ref_err < 1e-7
+    # the sketched residual tracks the true residual of the full model
+    u_full = a.cpu().numpy() @ rbo
+    true_res = sum(t * (A @ u_full) for t, A in zip(th, terms)) - f[0]
+    assert 0.5 < err / np.linalg.norm(true_res) < 1.5
