@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- sketch throughput of the B200 sketching engine (contract bench).
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm
+    python bench.py --impl reference --gpus N --steps K --warmup W # CPU reference arm
+    torchrun ... bench.py --gpus N ...                             # N > 1, one rank per GPU
+
+A step is one pass of the hot path over one block of synthetic vectors.  Workloads
+(BASELINE.json `configs`):
+    gauss_c2 (default)  Gaussian embedding k=2000 on a float64 2^22 x 512 block, Theta
+                        generated on the fly (configs[1]; FP64 tensor-pipe bound)
+    srht_c3             SRHT k=4000 on a float64 2^24 x 1024 block, column-sharded
+                        (configs[2]; HBM bound); run as the `secondary` result
+    srht_c1             SRHT k=1000 on 2^16 x 200 (configs[0], the reference's CPU case)
+Multi-GPU: column-sharded, no collective.  gauss_c2 scales weakly (every rank sketches its
+own 2^22 x 512 block); srht_c3 is the fixed 2^24 x 1024 block split by columns (strong).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "gauss_c2": dict(kind="gauss", m=512, logn=22, k=2000, config="configs[1]"),
+    "srht_c3": dict(kind="srht", m=1024, logn=24, k=4000, config="configs[2]"),
+    "srht_c1": dict(kind="srht", m=200, logn=16, k=1000, config="configs[0]"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gauss_c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary SRHT result")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ CPU reference legs
+def cpu_gauss_sample(U_host, k_total, k_block, seed=0):
+    """One row block of Theta in the reference's BlockGaussianEmbedding decomposition
+    (rla/embeddings.py:393-400,425-434,452-461): RandomState.normal + (Theta @ U^T)^T."""
+    from oracle import embeddings_oracle as eo
+    t0 = time.perf_counter()
+    theta = eo.block_gaussian_block(k_total, U_host.shape[1], k_block, seed)
+    y = (theta @ U_host.T).T
+    dt = time.perf_counter() - t0
+    return dt, float(np.abs(y).sum())
+
+
+def cpu_srht_sample(x_host, k, seed=0):
+    import oracle
+    t0 = time.perf_counter()
+    y = oracle.srht(x_host, k, seed=seed, nthreads=0)
+    return time.perf_counter() - t0, float(np.abs(y).sum())
+
+
+def host_block(m, n, seed=1234):
+    """Synthetic N(0,1) block on the host; a 16-vector base is tiled (values do not matter
+    for the CPU timing, generation of 17 GB of normals would dominate the run)."""
+    rs = np.random.RandomState(seed)
+    base = rs.standard_normal((min(m, 16), n))
+    reps = -(-m // base.shape[0])
+    return np.ascontiguousarray(np.tile(base, (reps, 1))[:m])
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU algorithm for the same workload on the host
+    cores of this box (oracle port: /root/reference is a Python tree that does not travel
+    to the GPU box, so its restatement under oracle/ is what runs here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    m, n, k = wl["m"], 2 ** wl["logn"], wl["k"]
+    cores = os.cpu_count() or 1
+    if wl["kind"] == "gauss":
+        kb = 50
+        U = host_block(m, n)
+        step = lambda: cpu_gauss_sample(U, k, kb)
+        sample = (f"one {kb}-row block of Theta (of {k}) over the full {m} x 2^{wl['logn']} block per step: "
+                  f"RandomState.normal + dgemm; whole-sketch time = step time x {k // kb}")
+        scale = k / kb
+        threads = blas_threads()
+    else:
+        ms = min(m, 8 if wl["logn"] >= 22 else m)
+        U = host_block(ms, n)
+        step = lambda: cpu_srht_sample(U, k)
+        sample = f"{ms} of {m} vectors per step (srht() incl. its per-call sign/index draw); rate scaled per vector"
+        scale = m / ms
+        threads = cores
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t = []
+    for _ in range(args.steps):
+        dt, _ = step()
+        t.append(dt)
+        if sum(t) > 240:
+            break
+    full = float(np.mean(t)) * scale                      # seconds for the whole block
+    gbs = m * n * 8 / full / 1e9
+    line = {
+        "impl": "reference", "metric": "sketch throughput", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": len(t), "warmup": min(args.warmup, 1), "ms_per_step": float(np.mean(t)) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "baseline_config": wl["config"], "m": m, "n": n, "k": k,
+                   "cols_per_s": m / full, "extrapolated": True},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
+                         "host_cpus": cores},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import rla4mor_b200 as rb
+    from rla4mor_b200 import dense
+    from rla4mor_b200.streaming import apply_streamed
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the sketching engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = rb.lib()
+    peaks, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def reduce_sum(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+        return x
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = lib.rla_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = lib.rla_launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        barrier()
+        return reduce_max(ms), int(reduce_sum(launches)), clocks
+
+    def run_workload(name, with_e2e, with_cpu, steps, warmup):
+        wl = WORKLOADS[name]
+        n, k = 2 ** wl["logn"], wl["k"]
+        strong = wl["kind"] == "srht" and name == "srht_c3"
+        m_total = wl["m"] if strong else wl["m"] * world
+        m_loc = wl["m"] // world if strong else wl["m"]
+        note = None
+        free, _ = torch.cuda.mem_get_info(dev)
+        fit = int((free - (6 << 30)) // (n * 8))
+        if m_loc > fit:
+            note = f"per-GPU block cut from {m_loc} to {fit} vectors to fit {free / 2**30:.0f} GiB free"
+            m_loc = fit
+            m_total = m_loc * world
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        U = torch.empty((m_loc, n), dtype=torch.float64, device=dev)
+        for lo in range(0, m_loc, 32):                      # in-place fill, no 2x temporary
+            U[lo:lo + 32].normal_(generator=gen)
+        out = torch.empty((m_loc, k), dtype=torch.float64, device=dev)
+        if wl["kind"] == "gauss":
+            emb = rb.GaussianEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k, "rng": "philox"}, _seed=0)
+            step = lambda: dense.embed_apply_rng(0, dense.KIND_NORMAL, 1.0 / np.sqrt(k), k, U, out=out)
+            apply_fn = emb.apply
+            work = 2.0 * k * n * m_loc                       # flops per rank per step
+            scratch = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+            import ctypes
+            pk = ctypes.c_double(0.0)
+            rb._lib.check(lib.rla_dmma_peak_tflops(ctypes.byref(pk), scratch.data_ptr(), rb._lib.stream_ptr()), "dmma peak")
+            a_cb = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+            for _ in range(2):
+                a_cb @ a_cb
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(); a_cb @ a_cb; c1.record(); torch.cuda.synchronize()
+            cublas_tf = 2 * 4096 ** 3 / c0.elapsed_time(c1) / 1e9
+            del a_cb
+            roof = dict(bound="tensor", unit="TFLOP/s", peak=pk.value,
+                        peak_source="in-run FP64 DMMA issue-rate microbenchmark (rla_dmma_peak_tflops); "
+                                    "MEASURED_PEAKS.json has no FP64 entry",
+                        cublas_dgemm_tflops_same_run=cublas_tf,
+                        algorithmic="2*k*n*m flops per launch, Theta generated in-kernel (no bytes)")
+        else:
+            emb = rb.SrhtEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k}, _seed=0)
+            plan = emb._plan(torch.float64, dev)
+            step = lambda: plan.apply(U, out=out)
+            apply_fn = emb.apply
+            work = float(m_loc * n * 8 + m_loc * k * 8 + n + 4 * k)   # algorithmic bytes per rank per step
+            roof = dict(bound="hbm", unit="GB/s", peak=float(peaks["hbm_gbs"]), peak_source=peak_src,
+                        algorithmic="m*n*8 (read U once) + m*k*8 (write sketch) + n (signs) + 4k (indices) bytes per launch")
+        ms, launches, clocks = timed(step, steps, warmup)
+        t_step = ms / steps / 1e3
+        achieved = work / t_step / (1e12 if roof["bound"] == "tensor" else 1e9)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(name)
+        roof.update(achieved=achieved, frac=achieved / roof["peak"], traffic=traffic,
+                    kernel="sketch_gemm_kernel" if wl["kind"] == "gauss" else "srht_main_kernel",
+                    note="duration = whole step (main kernel + its small reduce/finalize kernel), CUDA events")
+        res = {
+            "workload": name, "value": m_total * n * 8 / t_step / 1e9, "unit": "GB/s",
+            "cols_per_s": m_total / t_step, "ms_per_step": ms / steps, "gpu_launches": launches,
+            "roofline": roof, "clocks": clocks,
+            "config": {"workload": name, "baseline_config": wl["config"], "embedding": wl["kind"], "m_total": m_total,
+                       "m_per_gpu": m_loc, "n": n, "k": k, "partition": f"columns x{world} (no collective)",
+                       "scaling": "strong" if strong else "weak",
+                       "l2": "inputs larger than L2 (per-GPU block %.1f GB >> 126 MB)" % (m_loc * n * 8 / 1e9)},
+        }
+        if note:
+            res["config"]["note"] = note
+        # ---- end to end: host (pinned) block -> H2D -> sketch -> D2H of the result, per step
+        if with_e2e:
+            m_e = min(m_loc, max(1, (20 << 30) // (n * 8)))           # at most ~20 GiB of pinned memory
+            try:
+                host = torch.empty((m_e, n), dtype=torch.float64, pin_memory=True)
+                host.copy_(U[:m_e])
+                torch.cuda.synchronize()
+                rows = max(1, min(m_e, (1 << 30) // (n * 8)))
+                e_step = lambda: apply_streamed(apply_fn, host, k, rows_per_chunk=rows, return_host=True)
+                e_steps = max(2, min(steps, 5))
+                ems, _, _ = timed(e_step, e_steps, 1)
+                te = ems / e_steps / 1e3
+                res["e2e"] = {"value": m_e * world * n * 8 / te / 1e9, "unit": "GB/s",
+                              "h2d_bytes_per_step": int(m_e * n * 8), "d2h_bytes_per_step": int(m_e * k * 8),
+                              "api": f"{type(emb).__name__}.apply through streaming.apply_streamed (pinned host block, "
+                                     f"{rows}-vector chunks, copy/compute overlapped)",
+                              "m_per_gpu": m_e, "ms_per_step": ems / e_steps, "cols_per_s": m_e * world / te}
+                if rank == 0 and with_cpu:
+                    res["_host_block"] = host.numpy()
+                else:
+                    del host
+            except RuntimeError as exc:                               # pinned allocation refused
+                res["e2e"] = {"value": None, "unit": "GB/s", "error": str(exc)[:200]}
+        del U, out
+        torch.cuda.empty_cache()
+        return res
+
+    primary = run_workload(args.workload, not args.no_e2e, not args.no_cpu_baseline, args.steps, args.warmup)
+    host_block_np = primary.pop("_host_block", None)
+    secondary = []
+    if not args.no_secondary and args.workload == "gauss_c2":
+        secondary.append(run_workload("srht_c3", False, False, max(3, min(args.steps, 10)), max(3, args.warmup)))
+        secondary[-1].pop("_host_block", None)
+
+    cpu = None
+    if rank == 0 and world >= 1 and not args.no_cpu_baseline and args.gpus == 1:
+        wl = WORKLOADS[args.workload]
+        m, n, k = wl["m"], 2 ** wl["logn"], wl["k"]
+        if wl["kind"] == "gauss":
+            Uh = host_block_np if host_block_np is not None else host_block(m, n)
+            kb = 50
+            cpu_gauss_sample(Uh[:8], k, 2)                           # warm BLAS
+            dt, _ = cpu_gauss_sample(Uh, k, kb)
+            full = dt * (k / kb) * (m / Uh.shape[0])
+            cpu = {"value": m * n * 8 / full / 1e9, "unit": "GB/s", "cores": blas_threads(), "kind": "port",
+                   "sample": f"one {kb}-row Theta block (of {k}) over {Uh.shape[0]} x 2^{wl['logn']} vectors: "
+                             f"{dt:.1f} s; RandomState.normal (1 thread) + OpenBLAS dgemm; scaled x{k // kb}",
+                   "host_cpus": os.cpu_count(), "cols_per_s": m / full}
+        else:
+            ms_ = min(m, 8 if wl["logn"] >= 22 else m)
+            Uh = host_block(ms_, n)
+            cpu_srht_sample(Uh[:1, :4096].copy(), 16)
+            dt, _ = cpu_srht_sample(Uh, k)
+            full = dt * m / ms_
+            import oracle.srht_oracle as so
+            cpu = {"value": m * n * 8 / full / 1e9, "unit": "GB/s", "cores": so.oracle_threads(), "kind": "port",
+                   "sample": f"{ms_} of {m} vectors, srht() incl. its per-call sign/index draw: {dt:.1f} s; scaled per vector",
+                   "host_cpus": os.cpu_count(), "cols_per_s": m / full}
+
+    if rank == 0:
+        line = {
+            "metric": "sketch throughput", "value": primary["value"], "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": primary["ms_per_step"],
+            "higher_is_better": True, "scaling": primary["config"]["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": primary["config"], "cols_per_s": primary["cols_per_s"],
+            "clocks": primary["clocks"], "e2e": primary.get("e2e"), "gpu_launches": primary["gpu_launches"],
+            "roofline": primary["roofline"], "cpu_baseline": cpu,
+            "secondary": [{kk: vv for kk, vv in s.items() if kk != "e2e"} for s in secondary],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    assert args.warmup >= 0 and args.steps >= 1
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3                                            # timing rule: W >= 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

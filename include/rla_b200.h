@@ -121,6 +121,11 @@ int rla_srht_adjoint_f64(const int8_t *signs_dev, int64_t n, const int64_t *idx_
  */
 size_t rla_gemm_workspace_bytes(int64_t m, int64_t k, int64_t n);
 
+/* Measured FP64 tensor-pipe peak of the current device in TFLOP/s (independent
+ * mma.sync.m8n8k4.f64 issued back to back on every SM): the roofline denominator bench.py
+ * uses for the dense sketch.  scratch_dev: >= 1 MiB of device memory.  Synchronises. */
+int rla_dmma_peak_tflops(double *tflops, void *scratch_dev, void *stream);
+
 /* Theta materialised in device memory (drawn by the host exactly as
  * rla/embeddings.py:265-270 does). */
 int rla_gauss_apply_explicit_f64(const double *theta_dev, int64_t k, int64_t n, int64_t ldt,

@@ -280,6 +280,22 @@ __global__ void gemm_fallback_kernel(const double *__restrict__ u, int64_t ldu, 
     if (lane == 0) y[row * ldy + col] = s;
 }
 
+// back-to-back independent DMMAs: the FP64 tensor-pipe issue peak of this device
+__global__ void dmma_peak_kernel(double *out, int iters) {
+    double a = threadIdx.x * 1e-3 + 1.0, b = threadIdx.x * 1e-4 + 0.5;
+    double c[16][2];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { c[j][0] = 0.0; c[j][1] = 0.0; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dmma884(c[j][0], c[j][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += c[j][0] + c[j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 static PFN_cuTensorMapEncodeTiled get_encode() {
     static PFN_cuTensorMapEncodeTiled fn = nullptr;
     if (!fn) {
@@ -402,6 +418,31 @@ static int sketch_gemm(int mode, const double *theta, int64_t ldt, uint64_t seed
 }  // namespace rla
 
 using namespace rla;
+
+// Measured FP64 tensor-pipe peak (TFLOP/s) of the current device: 8 warps per SM issuing
+// independent mma.sync.m8n8k4.f64 back to back.  scratch_dev: >= 1 MiB.  Synchronises.
+extern "C" int rla_dmma_peak_tflops(double *tflops, void *scratch_dev, void *stream) {
+    RLA_REQUIRE(tflops && scratch_dev, "rla_dmma_peak_tflops: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = sm_count();
+    RLA_REQUIRE(sms * 256 * 8 <= 1024 * 1024, "rla_dmma_peak_tflops: scratch too small");
+    cudaEvent_t e0, e1;
+    RLA_CUDA_CHECK(cudaEventCreate(&e0));
+    RLA_CUDA_CHECK(cudaEventCreate(&e1));
+    const int iters = 20000;
+    dmma_peak_kernel<<<sms, 256, 0, st>>>(static_cast<double *>(scratch_dev), 200);
+    RLA_CUDA_CHECK(cudaEventRecord(e0, st));
+    dmma_peak_kernel<<<sms, 256, 0, st>>>(static_cast<double *>(scratch_dev), iters);
+    RLA_CUDA_CHECK(cudaEventRecord(e1, st));
+    RLA_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RLA_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flop = 2.0 * 8 * 8 * 4 * 16.0 * iters * 8.0 * sms;
+    *tflops = flop / (ms * 1e-3) / 1e12;
+    return RLA_OK;
+}
 
 extern "C" size_t rla_gemm_workspace_bytes(int64_t m, int64_t k, int64_t n) {
     if (m <= 0 || k <= 0 || n <= 0) return 0;

@@ -1,0 +1,117 @@
+"""Multi-GPU partitioning of the sketch (one process per GPU, torch.distributed).
+
+Two modes:
+
+* column-sharded (default): the m vectors of the block -- rows of the (m, n) array,
+  columns of the n x m matrix -- are split across ranks; the embedding descriptor
+  (seed, signs, indices) is replicated.  Units are independent: NO collective.  This is
+  the reference's only parallelism (numba prange over rows, rla/srht.py:93-96).
+
+* row-sharded (very tall n): the vector dimension is split into contiguous slabs, one
+  per rank; every rank sketches its slab and the (m, k) partial sketches are summed with
+  ONE all-reduce (NCCL over NVLink on GPUs).
+    - Gaussian / Rademacher: rank g applies Theta[:, slab_g] (column offset into the
+      virtual matrix).
+    - SRHT: H_{2^d} = H_G (x) H_{2^d/G} for a power-of-two world size G: rank g runs the
+      SRHT kernel on its slab with the low index bits s & (slab - 1) and its slice of the
+      signs, then flips sample i by (-1)^popcount((s_i >> log2 slab) & g).
+  Summation order differs from the single-GPU kernel, so results agree to rounding
+  (1e-15 relative), not bit for bit.
+
+The functions that touch data take the local sketch as a callable, so the host logic
+(partitioning, sign factors, the collective) is testable on CPU with the gloo backend.
+"""
+import numpy as np
+
+
+def column_shard(m, rank, world):
+    """Half-open range [lo, hi) of the vectors owned by `rank` (balanced, contiguous)."""
+    base, rem = divmod(int(m), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gaussian_slabs(n, world, align=16):
+    """Contiguous slabs of the vector dimension, boundaries multiples of `align`
+    (the GEMM kernel needs col0 % 16 == 0)."""
+    per = -(-int(n) // int(world))
+    per = -(-per // align) * align
+    return [(min(g * per, n), min((g + 1) * per, n)) for g in range(world)]
+
+
+def srht_slabs(n, world):
+    """Power-of-two slabs of the padded length 2^d; returns (slab_size, [(lo, hi)] clipped to n)."""
+    assert world & (world - 1) == 0, "row-sharded SRHT needs a power-of-two world size"
+    d = int(np.ceil(np.log2(n))) if n > 1 else 0
+    assert (1 << d) >= world, "more ranks than padded elements"
+    slab = (1 << d) // world
+    return slab, [(min(g * slab, n), min((g + 1) * slab, n)) for g in range(world)]
+
+
+def srht_slab_descriptor(signs, sampling, n, rank, world):
+    """What rank `rank` needs to sketch its slab with the ordinary SRHT kernel:
+    (lo, hi, local signs, local indices, +-1 factor per sample)."""
+    slab, ranges = srht_slabs(n, world)
+    lo, hi = ranges[rank]
+    s = np.asarray(sampling, dtype=np.int64)
+    local_idx = s & (slab - 1)
+    high = s // slab
+    par = np.zeros(len(s), dtype=np.int64)
+    v = high & rank
+    while np.any(v):
+        par ^= v & 1
+        v >>= 1
+    return lo, hi, np.asarray(signs)[lo:hi], local_idx, 1.0 - 2.0 * par
+
+
+def all_reduce_sum(t, group=None):
+    """Sum a tensor over the ranks (no-op without an initialised process group)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def row_sharded_sketch(local_sketch, factor=None, group=None):
+    """partial = local_sketch() [* factor per sample]; returns the all-reduced (m, k) sketch."""
+    part = local_sketch()
+    if factor is not None:
+        part = part * factor
+    return all_reduce_sum(part, group)
+
+
+# --------------------------------------------------------------------- device front ends
+def srht_row_sharded(x_slab, n, k, seed, rank, world, group=None):
+    """Row-sharded SRHT on the GPU: x_slab is this rank's (m, hi - lo) CUDA slab."""
+    import torch
+    from .srht import SrhtPlan, draw_signs_and_indices
+    signs, sampling = draw_signs_and_indices(n, k, seed)
+    lo, hi, lsigns, lidx, fac = srht_slab_descriptor(signs, sampling, n, rank, world)
+    m = x_slab.shape[0]
+    if hi <= lo:
+        part = torch.zeros((m, k), dtype=x_slab.dtype, device=x_slab.device)
+        return all_reduce_sum(part, group)
+    assert x_slab.shape[1] == hi - lo
+    slab = srht_slabs(n, world)[0]
+    if hi - lo < slab:
+        # ragged last slab: pad to the slab length so the local indices stay in range
+        xp = torch.zeros((m, slab), dtype=x_slab.dtype, device=x_slab.device)
+        xp[:, :hi - lo] = x_slab
+        x_slab = xp
+        lsigns = np.concatenate([lsigns, np.ones(slab - (hi - lo), dtype=lsigns.dtype)])
+    plan = SrhtPlan(x_slab.shape[1], k, lsigns, lidx, x_slab.dtype, x_slab.device)
+    fac_t = torch.as_tensor(fac, dtype=x_slab.dtype, device=x_slab.device)
+    return row_sharded_sketch(lambda: plan.apply(x_slab, scale=1.0 / np.sqrt(k)), fac_t, group)
+
+
+def gaussian_row_sharded(x_slab, n, k, seed, rank, world, kind=0, group=None):
+    """Row-sharded on-the-fly Gaussian / Rademacher sketch on the GPU."""
+    import torch
+    from . import dense
+    lo, hi = gaussian_slabs(n, world)[rank]
+    m = x_slab.shape[0]
+    if hi <= lo:
+        return all_reduce_sum(torch.zeros((m, k), dtype=torch.float64, device=x_slab.device), group)
+    assert x_slab.shape[1] == hi - lo
+    return row_sharded_sketch(lambda: dense.embed_apply_rng(seed, kind, 1.0 / np.sqrt(k), k, x_slab, col0=lo),
+                              None, group)

@@ -1,0 +1,58 @@
+"""Sketching blocks that live in HOST memory: the (m, n) block is cut into groups of
+vectors (rows), each group is copied host->device on a copy stream into one of two
+device staging buffers while the previous group is being sketched, and the (rows, k)
+results are written into one device tensor (optionally copied back to the host).
+
+This is the column blocking of the reference's `project_block`
+(utilities/utilities.py:114-121) turned into a copy/compute pipeline; vectors are
+independent, so no result depends on the grouping.
+"""
+import numpy as np
+import torch
+
+from ._lib import require_cuda
+
+
+def pinned_like(shape, dtype=torch.float64):
+    require_cuda()
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def apply_streamed(apply_fn, U_host, k, rows_per_chunk=None, out=None, device=None, return_host=False):
+    """apply_fn: CUDA (rows, n) tensor -> CUDA (rows, k) tensor (e.g. `embedding.apply`).
+    U_host: CPU torch tensor (pinned for full PCIe speed) or NumPy array, (m, n).
+    Returns the (m, k) sketch on the device (or a pinned host tensor if return_host)."""
+    require_cuda()
+    if isinstance(U_host, np.ndarray):
+        U_host = torch.from_numpy(np.ascontiguousarray(U_host))
+    assert not U_host.is_cuda and U_host.dim() == 2
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    m, n = U_host.shape
+    if rows_per_chunk is None:
+        rows_per_chunk = max(1, min(m, (1 << 30) // max(1, n * U_host.element_size())))   # ~1 GiB per chunk
+    if out is None:
+        out = torch.empty((m, k), dtype=U_host.dtype, device=device)
+    if m == 0:
+        return out
+    main = torch.cuda.current_stream(device)
+    copy = torch.cuda.Stream(device)
+    bufs = [torch.empty((rows_per_chunk, n), dtype=U_host.dtype, device=device) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    chunks = [(lo, min(lo + rows_per_chunk, m)) for lo in range(0, m, rows_per_chunk)]
+    for i, (lo, hi) in enumerate(chunks):
+        b = i & 1
+        with torch.cuda.stream(copy):
+            if i >= 2:
+                copy.wait_event(consumed[b])            # the sketch of chunk i-2 has read this buffer
+            bufs[b][:hi - lo].copy_(U_host[lo:hi], non_blocking=True)
+            copied[b].record(copy)
+        main.wait_event(copied[b])
+        out[lo:hi].copy_(apply_fn(bufs[b][:hi - lo]))
+        consumed[b].record(main)
+    if return_host:
+        host = torch.empty((m, k), dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        main.synchronize()
+        return host
+    return out
