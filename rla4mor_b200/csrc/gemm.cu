@@ -51,6 +51,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done;
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -131,7 +140,7 @@ sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
 
     if (warp >= GWARPS) {
         // ------------------------------------------------------------ producers
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         const int p = tid - GTHREADS;                  // 0..127: row of the Theta tile
         for (int it = 0; it < iters; ++it) {
             const int s = it % GSTAGES;
@@ -169,7 +178,7 @@ sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
     }
 
     // ---------------------------------------------------------------- consumers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / WN, wn = warp % WN;
     double acc[8][4][2];
@@ -184,40 +193,82 @@ sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
     const int64_t mg64 = (a.m - (m0 + wm * 64) + 7) / 8;
     const int mgroups = mg64 < 0 ? 0 : (mg64 > 8 ? 8 : (int)mg64);
 
-    for (int it = 0; it < iters; ++it) {
-        const int s = it % GSTAGES;
-        mbar_wait(&full_bar[s], (it / GSTAGES) & 1);
-        const double *At = reinterpret_cast<const double *>(smem + s * STAGE_BYTES) + (wm * 64) * GK;
-        const double *Bt = reinterpret_cast<const double *>(smem + s * STAGE_BYTES + A_BYTES) + (wn * 32) * GK;
-        double bf[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) lds_row4(Bt, 8 * j + g, t, bf[j]);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            double af[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) lds_row4(At, 8 * (4 * half + i) + g, t, af[i]);
-            if (half == 1) {
-                // all shared-memory reads of this stage are issued: release the slot
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
-            }
-            // kk outermost: consecutive DMMAs never hit the same accumulator
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (4 * half + i < mgroups) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (j < ngroups)
-                                dmma884(acc[4 * half + i][j][0], acc[4 * half + i][j][1], af[i][kk], bf[j][kk]);
-                        }
-                    }
-                }
-            }
+    // Fragments are held per 8-wide half of the 16-wide k block, double buffered: while the
+    // 64 DMMAs of one half issue, the 12 LDS.128 of the next half are in flight.  In half h
+    // a thread owns k = 4t + 2h + {0, 1} of every row: the 16-byte chunk 2t + h, XOR-swizzled
+    // with (row & 7) = g for every row this thread touches.
+    double2 a8[2][8], b8[2][4];
+    const uint32_t row_off = (uint32_t)g * 128u;
+    const uint32_t off0 = row_off + ((uint32_t)((2 * t) ^ g) << 4);
+    const uint32_t off1 = row_off + ((uint32_t)((2 * t + 1) ^ g) << 4);
+    const uint32_t a_warp = (uint32_t)(wm * 64) * 128u, b_warp = (uint32_t)A_BYTES + (uint32_t)(wn * 32) * 128u;
+#define LOAD_FRAGS(BUF, STAGE, OFF)                                                              \
+    {                                                                                            \
+        const unsigned char *sa_ = smem + (STAGE) * STAGE_BYTES + a_warp + (OFF);                \
+        const unsigned char *sb_ = smem + (STAGE) * STAGE_BYTES + b_warp + (OFF);                \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i)                                            \
+            a8[BUF][i] = *reinterpret_cast<const double2 *>(sa_ + i * 1024);                     \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j)                                            \
+            b8[BUF][j] = *reinterpret_cast<const double2 *>(sb_ + j * 1024);                     \
+    }
+#define MMA_HALF(BUF, PRED)                                                                      \
+    {                                                                                            \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                          \
+            if (!(PRED) || i < mgroups) {                                                        \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                  \
+                    if (!(PRED) || j < ngroups) dmma884(acc[i][j][0], acc[i][j][1], a8[BUF][i].x, b8[BUF][j].x); \
+                }                                                                                \
+            }                                                                                    \
+        }                                                                                        \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                          \
+            if (!(PRED) || i < mgroups) {                                                        \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                  \
+                    if (!(PRED) || j < ngroups) dmma884(acc[i][j][0], acc[i][j][1], a8[BUF][i].y, b8[BUF][j].y); \
+                }                                                                                \
+            }                                                                                    \
+        }                                                                                        \
+    }
+#define CONSUMER_LOOP(PRED)                                                                      \
+    for (int it = 0; it < iters; ++it) {                                                         \
+        const int s = it % GSTAGES;                                                              \
+        LOAD_FRAGS(1, s, off1);                                                                  \
+        const bool more = it + 1 < iters;                                                        \
+        const int sn = (it + 1) % GSTAGES;                                                       \
+        const uint32_t pn = ((it + 1) / GSTAGES) & 1;                                            \
+        uint32_t ready = 1;                                                                      \
+        if (more) ready = mbar_try_wait(&full_bar[sn], pn);   /* polled early, used after the DMMAs */ \
+        MMA_HALF(0, PRED);                                                                       \
+        if (more) {                                                                              \
+            while (!ready) ready = mbar_try_wait(&full_bar[sn], pn);                             \
+            LOAD_FRAGS(0, sn, off0);                                                             \
+        }                                                                                        \
+        MMA_HALF(1, PRED);                                                                       \
+        /* every shared-memory read of stage s has completed (its data fed the DMMAs above) */   \
+        __syncwarp();                                                                            \
+        if (lane == 0) mbar_arrive(&empty_bar[s]);                                               \
+    }
+
+    if (iters > 0) {
+        mbar_wait(&full_bar[0], 0);
+        LOAD_FRAGS(0, 0, off0);
+    }
+    // A warp with any row and column group inside the sketch runs the whole 64 x 32 warp tile
+    // without predicates or branches between the DMMAs: rows beyond m are zero-filled by TMA
+    // and columns beyond k are computed but never stored.  Warps entirely outside only keep
+    // the pipeline barriers moving.
+    if (mgroups > 0 && ngroups > 0) {
+        CONSUMER_LOOP(false)
+    } else {
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % GSTAGES;
+            if (it > 0) mbar_wait(&full_bar[s], (it / GSTAGES) & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
     }
+#undef CONSUMER_LOOP
+#undef LOAD_FRAGS
+#undef MMA_HALF
 
     // partial tile -> workspace [chunk][m][k]
     double *wsp = a.ws + chunk * a.m * a.k;
