@@ -132,6 +132,165 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Warp-specialised variant (default): one CTA of 384 threads per SM.
+//   threads   0..127  transform team X (two 64-thread tile groups): tile pairs 0, 2, 4, ...
+//   threads 128..255  transform team Y: tile pairs 1, 3, 5, ...
+//   threads 256..383  gather warps: own the NSLOT sample accumulators, serve X and Y in turn
+// A transform thread holds only its 64 tile elements (no accumulators), so the loads of its
+// next tile pair are issued right after the write-back of the current one and fly while the
+// gather warps read the tiles; the two teams run half an iteration apart, so one team's
+// FP64 butterflies overlap the other's shared-memory passes and load latency.  Teams and
+// gather warps hand the tile buffers back and forth with named barriers
+// (A_team: tiles ready, B_team: buffers free); setmaxnreg moves registers from the gather
+// warps (104) to the transform warps (200); 256*200 + 128*104 = 384*168, the launch allocation.
+constexpr int WS_THREADS = 3 * CTA;
+
+template <typename T, int NSLOT>
+__global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);                 // 4 tile buffers: team * 2 + group
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x / a.nchunks;
+    const int64_t chunk = blockIdx.x % a.nchunks;
+    const int64_t c0 = chunk << a.log2L;
+    const int npairs = 1 << (a.log2L - 1);
+
+    if (tid < 2 * CTA) {
+        // ------------------------------------------------------------ transform warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int team = tid >> 7, grp = (tid >> 6) & 1, tg = tid & 63;
+        const T *rowp = a.x + row * a.ldx;
+        T *buf = sm + (team * 2 + grp) * TILE;
+        auto tile_of = [&](int u) -> int64_t { return c0 + 2 * (int64_t)(u ^ (u >> 1)) + grp; };
+        auto is_fast = [&](int64_t jh) -> bool { return a.aligned && (jh + 1) * (int64_t)TILE <= a.n; };
+        auto gbar = [&]() {       // 64-thread barrier of this tile group: ids 1..4
+            if (team == 0) { if (grp == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory"); }
+            else { if (grp == 0) asm volatile("bar.sync 3, 64;" ::: "memory"); else asm volatile("bar.sync 4, 64;" ::: "memory"); }
+        };
+        T v[64];
+        uint64_t sw = 0;
+        // Rotated loop: ONE load site at the bottom (the loads of pair u + 2 are issued after
+        // pair u has been written back, and fly while the gather warps read it); the first
+        // trip (u < 0) only loads.  A second load site in a prologue makes the compiler merge
+        // the two register sets through local memory, which serialises the prefetch.
+        for (int u = team - 2; u < npairs; u += 2) {
+            bool loaded = false;
+            if (u >= 0) {
+                const int64_t jhA = c0 + 2 * (int64_t)(u ^ (u >> 1));
+                const int64_t jh = jhA + grp;
+                // B: the gather of this team's previous pair has finished reading the buffers
+                if (u >= 2) {
+                    if (team == 0) asm volatile("bar.sync 7, 256;" ::: "memory");
+                    else asm volatile("bar.sync 8, 256;" ::: "memory");
+                }
+                if (jhA < a.ntiles_valid) {
+                    if (jh < a.ntiles_valid && !is_fast(jh)) {
+                        const int64_t j0 = jh * TILE;
+#pragma unroll 4
+                        for (int e = tg; e < TILE; e += GROUP) buf[e] = (j0 + e < a.n) ? Elem<T>::load1(rowp + j0 + e) : T(0);
+                        gbar();
+#pragma unroll
+                        for (int h = 0; h < 32; ++h) { v[2 * h] = buf[128 * h + 2 * tg]; v[2 * h + 1] = buf[128 * h + 2 * tg + 1]; }
+                        gbar();
+                    }
+                    constexpr int M = Elem<T>::MASK;
+                    int tgo = tg;
+                    asm volatile("" : "+r"(tgo));              // keep the swizzled addresses out of LICM
+                    flip_and_butterflies64(v, sw);              // sign flip + tile bits 0, 7..11
+#pragma unroll
+                    for (int r = 0; r < 64; ++r) buf[r * 64 + (tgo ^ (r & M))] = v[r];
+                    gbar();
+#pragma unroll
+                    for (int r = 0; r < 64; ++r) v[r] = buf[tgo * 64 + (r ^ (tgo & M))];
+                    butterflies64(v);                           // tile bits 1..6
+                    // write-back; when the next tile of this group is a fast one, its loads are
+                    // issued pair by pair right behind the stores that free the registers
+                    const int64_t jn2 = tile_of(u + 2);
+                    if (u + 2 < npairs && jn2 < a.ntiles_valid && is_fast(jn2)) {
+                        const T *np_ = rowp + jn2 * TILE + 2 * tg;
+#pragma unroll
+                        for (int h = 0; h < 32; ++h) {
+                            buf[tgo * 64 + ((2 * h) ^ (tgo & M))] = v[2 * h];
+                            buf[tgo * 64 + ((2 * h + 1) ^ (tgo & M))] = v[2 * h + 1];
+                            Elem<T>::load2(np_ + 128 * h, v[2 * h], v[2 * h + 1]);
+                        }
+                        loaded = true;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 64; ++r) buf[tgo * 64 + (r ^ (tgo & M))] = v[r];
+                    }
+                }
+                // A: both transformed tiles of this team are in shared memory
+                if (team == 0) asm volatile("bar.arrive 5, 256;" ::: "memory");
+                else asm volatile("bar.arrive 6, 256;" ::: "memory");
+            }
+            if (u + 2 < npairs) {
+                const int64_t jn = tile_of(u + 2);
+                sw = (jn < a.ntiles_valid) ? __ldg(a.signw + jn * GROUP + tg) : 0ull;
+                // every path redefines all of v (so nothing of the old tile stays live): fast
+                // tiles are loaded here (or were, interleaved with the write-back above);
+                // ragged / unaligned tiles are staged later by the slow path; tiles beyond n
+                // inside a valid pair are zeros (virtual padding)
+                if (!loaded) {
+                    if (jn < a.ntiles_valid && is_fast(jn)) {
+                        load_tile_fast(v, rowp + jn * TILE, tg);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 64; ++r) v[r] = T(0);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------ gather warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    const int gt = tid - 2 * CTA;
+    uint32_t *sdesc = reinterpret_cast<uint32_t *>(sm + 4 * TILE) + gt;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) sdesc[s * CTA] = __ldg(a.desc + s * CTA + gt);
+    T acc[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) acc[s] = T(0);
+    for (int u = 0; u < npairs; ++u) {
+        const int64_t jhA = c0 + 2 * (int64_t)(u ^ (u >> 1));
+        const int fl_shift = 31 - (13 + (u ? __ffs(u) - 1 : 0));
+        const int team = u & 1;
+        if (team == 0) asm volatile("bar.sync 5, 256;" ::: "memory");
+        else asm volatile("bar.sync 6, 256;" ::: "memory");
+        if (jhA < a.ntiles_valid) {
+            const T *tb = sm + team * 2 * TILE;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+                const uint32_t dsc = sdesc[s * CTA];
+                const int off = dsc & (TILE - 1);
+                const T vA = tb[off], vB = tb[TILE + off];
+                const T w = vA + xor_sign(vB, dsc << 19);            // bit 12 = sh bit 0
+                acc[s] = xor_sign(acc[s], dsc << fl_shift) + w;
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) acc[s] = xor_sign(acc[s], sdesc[s * CTA] << fl_shift);
+        }
+        if (u + 2 < npairs) {                                        // somebody will wait for it
+            if (team == 0) asm volatile("bar.arrive 7, 256;" ::: "memory");
+            else asm volatile("bar.arrive 8, 256;" ::: "memory");
+        }
+    }
+    // accumulators are relative to the sign of the last A tile: undo it
+    const int glast = (npairs - 1) ^ ((npairs - 1) >> 1);
+    const uint32_t jlast = (uint32_t)(c0 + 2 * (int64_t)glast);
+    T *wsp = a.ws + ((chunk * a.m + row) * (int64_t)(NSLOT * CTA));
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const uint32_t dsc = sdesc[s * CTA];
+        const uint32_t par = __popc((dsc >> TILE_LOG2) & jlast) & 1u;
+        wsp[s * CTA + gt] = xor_sign(acc[s], par << 31);
+    }
+}
+
 // y[row, i] = scale * sum_chunks ws[pass(i)][chunk][row][slot(i)]
 template <typename T>
 __global__ void srht_finalize_kernel(const T *__restrict__ ws, const int32_t *__restrict__ slotmap,
@@ -268,8 +427,11 @@ extern "C" int rla_srht_plan_upload(rla_srht_plan *p, void *plan_dev, void *stre
     return RLA_OK;
 }
 
-// tiles per CTA: enough CTAs for >= 16 waves when the problem is large, but at least
-// 4 tiles per CTA so the partial-sketch write stays small next to the tile reads.
+static int srht_variant_for(int nslot);
+
+// tiles per CTA (a power of two): as many as possible while the grid still has ~8 waves of
+// CTAs, so the per-CTA prologue / drain and the partial-sketch write stay small next to the
+// tile reads, and never fewer than 4 tiles when the row has them.
 static int choose_log2L(const rla_srht_plan *p, int64_t m) {
     static int forced = -2;
     if (forced == -2) {
@@ -279,7 +441,8 @@ static int choose_log2L(const rla_srht_plan *p, int64_t m) {
     int maxl = 0;
     while ((int64_t(1) << (maxl + 1)) <= p->ntiles) ++maxl;
     if (forced >= 1) return std::min(forced, maxl);
-    const int64_t target = (int64_t)sm_count() * 2 * 16;
+    const int ctas_per_sm = srht_variant_for(p->nslot) == 0 ? 1 : 2;
+    const int64_t target = (int64_t)sm_count() * ctas_per_sm * 8;
     const int64_t total = m * p->ntiles_valid;
     int l = 1;
     while (l < maxl && (total >> (l + 1)) >= target) ++l;
@@ -320,8 +483,33 @@ static int launch_main_pf(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
     return RLA_OK;
 }
 
+// 0: warp-specialised 384-thread CTAs (default for >= 16 accumulators per thread);
+// 1: single-role 128-thread CTAs, two per SM (better when the accumulators are few and
+//    leave room for the compiler to overlap)
+static int srht_variant_for(int nslot) {
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("RLA_SRHT_VARIANT");
+        v = e ? atoi(e) : -1;
+    }
+    if (v >= 0) return v;
+    return nslot >= 16 ? 0 : 1;
+}
+
+template <typename T, int NSLOT>
+static int launch_ws(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
+    auto kern = srht_ws_kernel<T, NSLOT>;
+    const int smem = 4 * TILE * sizeof(T) + NSLOT * CTA * 4;
+    RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)grid, WS_THREADS, smem, st>>>(a);
+    count_launch();
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
+
 template <typename T, int NSLOT>
 static int launch_main(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
+    if (srht_variant_for(NSLOT) == 0) return launch_ws<T, NSLOT>(a, grid, st);
     return use_prefetch() ? launch_main_pf<T, NSLOT, true>(a, grid, st)
                           : launch_main_pf<T, NSLOT, false>(a, grid, st);
 }

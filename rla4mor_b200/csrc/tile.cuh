@@ -56,6 +56,34 @@ __device__ __forceinline__ void butterflies64(T (&v)[64]) {
     }
 }
 
+// Rademacher sign flip (srht.py:165) fused with the first butterfly stage (register bit 0):
+// the two sign masks of a pair are formed right where they are used, which keeps the
+// register pressure of the flip at a handful of temporaries.  Then stages 1..5.
+template <typename T>
+__device__ __forceinline__ void flip_and_butterflies64(T (&v)[64], uint64_t sw) {
+    const uint32_t lo = (uint32_t)sw, hi = (uint32_t)(sw >> 32);
+#pragma unroll
+    for (int h = 0; h < 32; ++h) {
+        const uint32_t w = h < 16 ? lo : hi;
+        const int b = (2 * h) & 31;
+        const T x = xor_sign(v[2 * h], w << (31 - b));
+        const T y = xor_sign(v[2 * h + 1], w << (30 - b));
+        v[2 * h] = x + y;
+        v[2 * h + 1] = x - y;
+    }
+#pragma unroll
+    for (int b = 1; b < 6; ++b) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            if ((i & (1 << b)) == 0) {
+                T p = v[i], q = v[i | (1 << b)];
+                v[i] = p + q;
+                v[i | (1 << b)] = p - q;
+            }
+        }
+    }
+}
+
 // 64-thread barrier of one tile group (ids 1 and 2; id 0 is __syncthreads)
 __device__ __forceinline__ void group_barrier(int grp) {
     if (grp == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
