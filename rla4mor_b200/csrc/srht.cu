@@ -134,65 +134,67 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
 
 // ---------------------------------------------------------------------------
 // Warp-specialised variant (default): one CTA of 384 threads per SM.
-//   threads   0..127  transform team X (two 64-thread tile groups): tile pairs 0, 2, 4, ...
-//   threads 128..255  transform team Y: tile pairs 1, 3, 5, ...
-//   threads 256..383  gather warps: own the NSLOT sample accumulators, serve X and Y in turn
+//   threads   0..255  four independent 64-thread transform groups; group q owns tile buffer q
+//                     and the tiles t = q, q+4, q+8, ... of the CTA's Gray-code tile sequence
+//   threads 256..383  gather warps: own the NSLOT sample accumulators, serve the four
+//                     buffers in tile order
 // A transform thread holds only its 64 tile elements (no accumulators), so the loads of its
-// next tile pair are issued right after the write-back of the current one and fly while the
-// gather warps read the tiles; the two teams run half an iteration apart, so one team's
-// FP64 butterflies overlap the other's shared-memory passes and load latency.  Teams and
-// gather warps hand the tile buffers back and forth with named barriers
-// (A_team: tiles ready, B_team: buffers free); setmaxnreg moves registers from the gather
-// warps (104) to the transform warps (200); 256*200 + 128*104 = 384*168, the launch allocation.
+// next tile are issued right behind the write-back stores of the current one and fly while
+// the gather warps read it.  The four groups drift freely (each meets only the gather warps,
+// through two named barriers per group: A_q "tile ready", B_q "buffer free"), so one group's
+// FP64 butterflies overlap another's shared-memory passes and a third's load latency.
+// setmaxnreg moves registers from the gather warps (104) to the transform warps (200);
+// 256*200 + 128*104 = 384*168, the launch allocation.
 constexpr int WS_THREADS = 3 * CTA;
+constexpr int WS_GROUPS = 4;
+
+__device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 template <typename T, int NSLOT>
 __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);                 // 4 tile buffers: team * 2 + group
+    T *sm = reinterpret_cast<T *>(smem_raw);                 // 4 tile buffers
     const int tid = threadIdx.x;
     const int64_t row = blockIdx.x / a.nchunks;
     const int64_t chunk = blockIdx.x % a.nchunks;
     const int64_t c0 = chunk << a.log2L;
-    const int npairs = 1 << (a.log2L - 1);
+    const int ntl = 1 << a.log2L;                            // tiles of this CTA
+    // barrier ids: 1..4 group-internal (64), 5..8 A_q, 9..12 B_q (64 + 128 = 192 threads)
 
     if (tid < 2 * CTA) {
         // ------------------------------------------------------------ transform warps
         asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-        const int team = tid >> 7, grp = (tid >> 6) & 1, tg = tid & 63;
+        const int q = tid >> 6, tg = tid & 63;
         const T *rowp = a.x + row * a.ldx;
-        T *buf = sm + (team * 2 + grp) * TILE;
-        auto tile_of = [&](int u) -> int64_t { return c0 + 2 * (int64_t)(u ^ (u >> 1)) + grp; };
+        T *buf = sm + q * TILE;
+        auto tile_of = [&](int t) -> int64_t { return c0 + (int64_t)(t ^ (t >> 1)); };
         auto is_fast = [&](int64_t jh) -> bool { return a.aligned && (jh + 1) * (int64_t)TILE <= a.n; };
-        auto gbar = [&]() {       // 64-thread barrier of this tile group: ids 1..4
-            if (team == 0) { if (grp == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory"); }
-            else { if (grp == 0) asm volatile("bar.sync 3, 64;" ::: "memory"); else asm volatile("bar.sync 4, 64;" ::: "memory"); }
-        };
         T v[64];
         uint64_t sw = 0;
-        // Rotated loop: ONE load site at the bottom (the loads of pair u + 2 are issued after
-        // pair u has been written back, and fly while the gather warps read it); the first
-        // trip (u < 0) only loads.  A second load site in a prologue makes the compiler merge
-        // the two register sets through local memory, which serialises the prefetch.
-        for (int u = team - 2; u < npairs; u += 2) {
+        // Rotated loop with ONE load site per path: the loads of tile t + 4 are issued behind
+        // the write-back of tile t; the first trip (t < 0) only loads.  (A second load site in
+        // a prologue makes the compiler merge the two register sets through local memory,
+        // which serialises the prefetch.)
+        for (int t = q - WS_GROUPS; t < ntl; t += WS_GROUPS) {
             bool loaded = false;
-            if (u >= 0) {
-                const int64_t jhA = c0 + 2 * (int64_t)(u ^ (u >> 1));
-                const int64_t jh = jhA + grp;
-                // B: the gather of this team's previous pair has finished reading the buffers
-                if (u >= 2) {
-                    if (team == 0) asm volatile("bar.sync 7, 256;" ::: "memory");
-                    else asm volatile("bar.sync 8, 256;" ::: "memory");
-                }
-                if (jhA < a.ntiles_valid) {
-                    if (jh < a.ntiles_valid && !is_fast(jh)) {
+            if (t >= 0) {
+                const int64_t jh = tile_of(t);
+                // B_q: the gather of this group's previous tile has finished reading the buffer
+                if (t >= WS_GROUPS) bar_sync(9 + q, 192);
+                if (jh < a.ntiles_valid) {
+                    if (!is_fast(jh)) {
                         const int64_t j0 = jh * TILE;
 #pragma unroll 4
                         for (int e = tg; e < TILE; e += GROUP) buf[e] = (j0 + e < a.n) ? Elem<T>::load1(rowp + j0 + e) : T(0);
-                        gbar();
+                        bar_sync(1 + q, 64);
 #pragma unroll
                         for (int h = 0; h < 32; ++h) { v[2 * h] = buf[128 * h + 2 * tg]; v[2 * h + 1] = buf[128 * h + 2 * tg + 1]; }
-                        gbar();
+                        bar_sync(1 + q, 64);
                     }
                     constexpr int M = Elem<T>::MASK;
                     int tgo = tg;
@@ -200,14 +202,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
                     flip_and_butterflies64(v, sw);              // sign flip + tile bits 0, 7..11
 #pragma unroll
                     for (int r = 0; r < 64; ++r) buf[r * 64 + (tgo ^ (r & M))] = v[r];
-                    gbar();
+                    bar_sync(1 + q, 64);
 #pragma unroll
                     for (int r = 0; r < 64; ++r) v[r] = buf[tgo * 64 + (r ^ (tgo & M))];
                     butterflies64(v);                           // tile bits 1..6
                     // write-back; when the next tile of this group is a fast one, its loads are
                     // issued pair by pair right behind the stores that free the registers
-                    const int64_t jn2 = tile_of(u + 2);
-                    if (u + 2 < npairs && jn2 < a.ntiles_valid && is_fast(jn2)) {
+                    const int64_t jn2 = tile_of(t + WS_GROUPS);
+                    if (t + WS_GROUPS < ntl && jn2 < a.ntiles_valid && is_fast(jn2)) {
                         const T *np_ = rowp + jn2 * TILE + 2 * tg;
 #pragma unroll
                         for (int h = 0; h < 32; ++h) {
@@ -221,17 +223,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
                         for (int r = 0; r < 64; ++r) buf[tgo * 64 + (r ^ (tgo & M))] = v[r];
                     }
                 }
-                // A: both transformed tiles of this team are in shared memory
-                if (team == 0) asm volatile("bar.arrive 5, 256;" ::: "memory");
-                else asm volatile("bar.arrive 6, 256;" ::: "memory");
+                // A_q: the transformed tile is in shared memory
+                bar_arrive(5 + q, 192);
             }
-            if (u + 2 < npairs) {
-                const int64_t jn = tile_of(u + 2);
+            if (t + WS_GROUPS < ntl) {
+                const int64_t jn = tile_of(t + WS_GROUPS);
                 sw = (jn < a.ntiles_valid) ? __ldg(a.signw + jn * GROUP + tg) : 0ull;
-                // every path redefines all of v (so nothing of the old tile stays live): fast
-                // tiles are loaded here (or were, interleaved with the write-back above);
-                // ragged / unaligned tiles are staged later by the slow path; tiles beyond n
-                // inside a valid pair are zeros (virtual padding)
+                // every path redefines all of v (nothing of the old tile stays live): fast tiles
+                // are loaded here (or were, interleaved with the write-back above); ragged /
+                // unaligned tiles are staged later by the slow path
                 if (!loaded) {
                     if (jn < a.ntiles_valid && is_fast(jn)) {
                         load_tile_fast(v, rowp + jn * TILE, tg);
@@ -248,40 +248,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
     // ------------------------------------------------------------------ gather warps
     asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     const int gt = tid - 2 * CTA;
-    uint32_t *sdesc = reinterpret_cast<uint32_t *>(sm + 4 * TILE) + gt;
+    uint32_t *sdesc = reinterpret_cast<uint32_t *>(sm + WS_GROUPS * TILE) + gt;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) sdesc[s * CTA] = __ldg(a.desc + s * CTA + gt);
     T acc[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) acc[s] = T(0);
-    for (int u = 0; u < npairs; ++u) {
-        const int64_t jhA = c0 + 2 * (int64_t)(u ^ (u >> 1));
-        const int fl_shift = 31 - (13 + (u ? __ffs(u) - 1 : 0));
-        const int team = u & 1;
-        if (team == 0) asm volatile("bar.sync 5, 256;" ::: "memory");
-        else asm volatile("bar.sync 6, 256;" ::: "memory");
-        if (jhA < a.ntiles_valid) {
-            const T *tb = sm + team * 2 * TILE;
+    for (int t = 0; t < ntl; ++t) {
+        const int64_t jh = c0 + (int64_t)(t ^ (t >> 1));
+        // moving from tile t-1 to t flips bit ctz(t) of the tile index = desc bit 12 + ctz(t)
+        const int fl_shift = 31 - (12 + (t ? __ffs(t) - 1 : 0));
+        const int q = t & (WS_GROUPS - 1);
+        bar_sync(5 + q, 192);
+        if (jh < a.ntiles_valid) {
+            const T *tb = sm + q * TILE;
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
                 const uint32_t dsc = sdesc[s * CTA];
-                const int off = dsc & (TILE - 1);
-                const T vA = tb[off], vB = tb[TILE + off];
-                const T w = vA + xor_sign(vB, dsc << 19);            // bit 12 = sh bit 0
-                acc[s] = xor_sign(acc[s], dsc << fl_shift) + w;
+                acc[s] = xor_sign(acc[s], dsc << fl_shift) + tb[dsc & (TILE - 1)];
             }
         } else {
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) acc[s] = xor_sign(acc[s], sdesc[s * CTA] << fl_shift);
         }
-        if (u + 2 < npairs) {                                        // somebody will wait for it
-            if (team == 0) asm volatile("bar.arrive 7, 256;" ::: "memory");
-            else asm volatile("bar.arrive 8, 256;" ::: "memory");
-        }
+        if (t + WS_GROUPS < ntl) bar_arrive(9 + q, 192);               // somebody will wait for it
     }
-    // accumulators are relative to the sign of the last A tile: undo it
-    const int glast = (npairs - 1) ^ ((npairs - 1) >> 1);
-    const uint32_t jlast = (uint32_t)(c0 + 2 * (int64_t)glast);
+    // accumulators are relative to the sign of the last tile: undo it
+    const uint32_t jlast = (uint32_t)(c0 + (int64_t)((ntl - 1) ^ ((ntl - 1) >> 1)));
     T *wsp = a.ws + ((chunk * a.m + row) * (int64_t)(NSLOT * CTA));
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
