@@ -198,13 +198,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
                     }
                     constexpr int M = Elem<T>::MASK;
                     int tgo = tg;
-                    asm volatile("" : "+r"(tgo));              // keep the swizzled addresses out of LICM
+                    asm volatile("" : "+r"(tgo));              // opaque: bounds what LICM can hoist
                     flip_and_butterflies64(v, sw);              // sign flip + tile bits 0, 7..11
+                    // the M + 1 swizzled column offsets of this thread, shared by the three passes
+                    const T *so[M + 1];
 #pragma unroll
-                    for (int r = 0; r < 64; ++r) buf[r * 64 + (tgo ^ (r & M))] = v[r];
+                    for (int c = 0; c <= M; ++c) so[c] = buf + (tgo ^ c);
+#pragma unroll
+                    for (int r = 0; r < 64; ++r) const_cast<T *>(so[r & M])[r * 64] = v[r];
                     bar_sync(1 + q, 64);
+                    const T *rb = buf + tgo * 64;
+                    int sx[M + 1];
 #pragma unroll
-                    for (int r = 0; r < 64; ++r) v[r] = buf[tgo * 64 + (r ^ (tgo & M))];
+                    for (int c = 0; c <= M; ++c) sx[c] = c ^ (tgo & M);
+#pragma unroll
+                    for (int r = 0; r < 64; ++r) v[r] = rb[(r & ~M) + sx[r & M]];
                     butterflies64(v);                           // tile bits 1..6
                     // write-back; when the next tile of this group is a fast one, its loads are
                     // issued pair by pair right behind the stores that free the registers
@@ -213,14 +221,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
                         const T *np_ = rowp + jn2 * TILE + 2 * tg;
 #pragma unroll
                         for (int h = 0; h < 32; ++h) {
-                            buf[tgo * 64 + ((2 * h) ^ (tgo & M))] = v[2 * h];
-                            buf[tgo * 64 + ((2 * h + 1) ^ (tgo & M))] = v[2 * h + 1];
+                            const_cast<T *>(rb)[((2 * h) & ~M) + sx[(2 * h) & M]] = v[2 * h];
+                            const_cast<T *>(rb)[((2 * h + 1) & ~M) + sx[(2 * h + 1) & M]] = v[2 * h + 1];
                             Elem<T>::load2(np_ + 128 * h, v[2 * h], v[2 * h + 1]);
                         }
                         loaded = true;
                     } else {
 #pragma unroll
-                        for (int r = 0; r < 64; ++r) buf[tgo * 64 + (r ^ (tgo & M))] = v[r];
+                        for (int r = 0; r < 64; ++r) const_cast<T *>(rb)[(r & ~M) + sx[r & M]] = v[r];
                     }
                 }
                 // A_q: the transformed tile is in shared memory
