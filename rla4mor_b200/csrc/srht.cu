@@ -428,7 +428,7 @@ extern "C" int rla_srht_plan_upload(rla_srht_plan *p, void *plan_dev, void *stre
     return RLA_OK;
 }
 
-static int srht_variant_for(int nslot);
+static int srht_variant_for(int64_t total_tiles);
 
 // tiles per CTA (a power of two): as many as possible while the grid still has ~8 waves of
 // CTAs, so the per-CTA prologue / drain and the partial-sketch write stay small next to the
@@ -442,9 +442,9 @@ static int choose_log2L(const rla_srht_plan *p, int64_t m) {
     int maxl = 0;
     while ((int64_t(1) << (maxl + 1)) <= p->ntiles) ++maxl;
     if (forced >= 1) return std::min(forced, maxl);
-    const int ctas_per_sm = srht_variant_for(p->nslot) == 0 ? 1 : 2;
-    const int64_t target = (int64_t)sm_count() * ctas_per_sm * 8;
     const int64_t total = m * p->ntiles_valid;
+    const int ctas_per_sm = srht_variant_for(total) == 0 ? 1 : 2;
+    const int64_t target = (int64_t)sm_count() * ctas_per_sm * 8;
     int l = 1;
     while (l < maxl && (total >> (l + 1)) >= target) ++l;
     if (l < 2 && maxl >= 2) l = 2;
@@ -484,17 +484,17 @@ static int launch_main_pf(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
     return RLA_OK;
 }
 
-// 0: warp-specialised 384-thread CTAs (default for >= 16 accumulators per thread);
-// 1: single-role 128-thread CTAs, two per SM (better when the accumulators are few and
-//    leave room for the compiler to overlap)
-static int srht_variant_for(int nslot) {
+// 0: warp-specialised 384-thread CTAs, one per SM (default);
+// 1: single-role 128-thread CTAs, two per SM: shorter prologue, better for tiny problems
+//    (a few tiles per SM), where launch and drain dominate
+static int srht_variant_for(int64_t total_tiles) {
     static int v = -2;
     if (v == -2) {
         const char *e = getenv("RLA_SRHT_VARIANT");
         v = e ? atoi(e) : -1;
     }
     if (v >= 0) return v;
-    return nslot >= 16 ? 0 : 1;
+    return total_tiles >= 16384 ? 0 : 1;
 }
 
 template <typename T, int NSLOT>
@@ -510,7 +510,7 @@ static int launch_ws(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
 
 template <typename T, int NSLOT>
 static int launch_main(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
-    if (srht_variant_for(NSLOT) == 0) return launch_ws<T, NSLOT>(a, grid, st);
+    if (srht_variant_for(a.m * a.ntiles_valid) == 0) return launch_ws<T, NSLOT>(a, grid, st);
     return use_prefetch() ? launch_main_pf<T, NSLOT, true>(a, grid, st)
                           : launch_main_pf<T, NSLOT, false>(a, grid, st);
 }
