@@ -211,6 +211,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries only the JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = rb.lib()
     peaks, peak_src = measured_peaks()

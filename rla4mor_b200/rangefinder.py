@@ -1,0 +1,42 @@
+"""Sketched randomized range finder (BASELINE.json configs[4]): sketch a block of m vectors
+of dimension n with Theta (k x n), then factor the small k x m sketch.
+
+    S = Theta U^T            (the (m, k) row block `Theta.apply(U)`)
+    S^T = Q R                Gram-Schmidt of the sketched vectors (as the reference's
+                             SketchedReductor does, mor/sketched_reductor.py:94-95), T = pinv(R)
+    or  S = V^T diag(s) W    one-sided Jacobi SVD of the sketch
+
+`U T^T` (rows: T^T @ U) is then a basis whose SKETCH is orthonormal; the singular values of
+the sketch estimate those of U to the embedding's (1 +- eps).  With `world > 1` the vector
+dimension is row-sharded: every rank sketches its slab and the (m, k) partial sketches are
+summed by one all-reduce (sharding.py); the small factorisation is replicated.
+"""
+import numpy as np
+import torch
+
+from . import reductor_ops as ops
+from . import sharding
+
+
+def sketch_block(U_local, n, k, seed, kind="srht", rank=0, world=1, group=None):
+    """(m, k) sketch of the block whose slab `U_local` (m, hi - lo) lives on this rank."""
+    if world == 1:
+        if kind == "srht":
+            from .srht import get_plan
+            return get_plan(n, k, seed, U_local.dtype, U_local.device).apply(U_local)
+        from . import dense
+        return dense.embed_apply_rng(seed, 1 if kind == "rademacher" else 0, 1.0 / np.sqrt(k), k, U_local)
+    if kind == "srht":
+        return sharding.srht_row_sharded(U_local, n, k, seed, rank, world, group)
+    return sharding.gaussian_row_sharded(U_local, n, k, seed, rank, world, 1 if kind == "rademacher" else 0, group)
+
+
+def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, group=None, svd=True):
+    """Returns dict(sketch, Q, R, T[, s, W]) -- all small (m x k, m x m) device tensors."""
+    S = sketch_block(U_local, n, k, seed, kind, rank, world, group)
+    Q, R = ops.gram_schmidt(S)
+    out = {"sketch": S, "Q": Q, "R": R, "T": torch.linalg.pinv(R)}
+    if svd:
+        Urows, s, W = ops.svd_jacobi(S, want_v=True)
+        out.update(s=s, W=W, Urows=Urows)
+    return out

@@ -141,3 +141,53 @@ def test_sketched_reductor_pipeline(rb, kind):
     u_full = a.cpu().numpy() @ rbo
     true_res = sum(t * (A @ u_full) for t, A in zip(th, terms)) - f[0]
     assert 0.5 < err / np.linalg.norm(true_res) < 1.5
+
+
+def test_range_finder_small(rb):
+    from rla4mor_b200.rangefinder import sketched_range_finder
+    rs = np.random.RandomState(0)
+    m, n, k, r = 24, 30000, 256, 6
+    U = (rs.standard_normal((m, r)) * np.logspace(0, -3, r)) @ rs.standard_normal((r, n)) + 1e-9 * rs.standard_normal((m, n))
+    Ud = _dev(U)
+    for kind in ("srht", "gauss"):
+        res = sketched_range_finder(Ud, n, k, seed=1, kind=kind)
+        s_true = np.linalg.svd(U, compute_uv=False)
+        s = res["s"].cpu().numpy()
+        assert np.all(np.abs(s[:r] / s_true[:r] - 1.0) < 0.35)           # (1 +- eps) embedding of the range
+        assert s[r] / s[0] < 1e-6                                         # numerical rank revealed
+        Q = res["Q"].cpu().numpy()
+        assert rel_fro(Q @ Q.T, np.eye(Q.shape[0])) < 1e-10
+        # oracle parity of the factorisation on the same sketch
+        Qo, Ro = ro.gram_schmidt(res["sketch"].cpu().numpy())
+        assert Q.shape == Qo.shape and rel_fro(res["R"].cpu().numpy(), Ro) < 1e-8
+
+
+def test_sketched_reductor_at_fem_size(rb):
+    """configs[3]-sized problem: n ~ 1e6, Q = 4 affine terms; checked through properties
+    (the oracle sketches only a few vectors at this size)."""
+    terms, n = _fem_terms(1000)                                           # n = 1e6, ~5 nnz/row
+    k, m = 1000, 16
+    space = rb.DeviceVectorSpace(n, id="STATE")
+    ops_dev = [rb.MatrixOperator(A, source_id="STATE", range_id="STATE") for A in terms]
+    emb = rb.SrhtEmbedding(source=space, options={"range_dim": k}, _seed=3)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    U = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    f = [torch.randn(n, dtype=torch.float64, device="cuda", generator=g)]
+    red = rb.SketchedReductor(ops_dev, f, emb)
+    red.extend_basis(U)
+    assert red.srb.shape == (m, k) and all(V.shape == (m, k) for V in red.s_lhs)
+    # sketched basis orthonormal, sketch of the transformed basis equals the transformed sketch
+    assert float(torch.linalg.norm(red.srb @ red.srb.T - torch.eye(m, device="cuda", dtype=torch.float64))) < 1e-10
+    assert float(torch.linalg.norm(emb.apply(red.rb) - red.srb) / torch.linalg.norm(red.srb)) < 1e-10
+    # one affine term against the oracle on two vectors
+    from oracle import embeddings_oracle as eo
+    v = red.rb[:2].cpu().numpy()
+    ref = eo.srht_apply(np.asarray((terms[1] @ v.T).T), k, 3)
+    assert rel_fro(red.s_lhs[1][:2].cpu().numpy(), ref) < 1e-11
+    rom = red.reduce()
+    th = [1.0, 0.7, 1.3, 0.2]
+    a = rom.solve(th, [1.0])
+    err = rom.estimate_error(a, th, [1.0])
+    u_full = a @ red.rb
+    true_res = sum(t * op.apply(space.from_numpy(u_full.reshape(1, -1))).data[0] for t, op in zip(th, ops_dev)) - f[0]
+    assert 0.8 < err / float(torch.linalg.norm(true_res)) < 1.2           # k = 1000 embedding of one vector
