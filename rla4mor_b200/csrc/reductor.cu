@@ -70,26 +70,41 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
 // Gram-Schmidt, re-iterated while the norm drops below reiteration_threshold * old norm;
 // R[j, i] += <A_j, A_i>, R[i, i] = final norm; a row whose norm falls below
 // rtol * initial (or atol initially) is flagged as removed and skipped afterwards.
-// One CTA; the row being orthogonalised lives in registers (EPT elements per thread).
-template <int EPT>
-__global__ void __launch_bounds__(256, 1)
+// One CTA of W warps; the row being orthogonalised lives in registers (EPT <= 16 elements
+// per thread), the next basis row is prefetched while the current dot product is reduced
+// (warp shuffles + one barrier per step), so a step costs a few hundred cycles.
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 gram_schmidt_kernel(double *__restrict__ A, int64_t r, int64_t k, int64_t lda, int64_t offset,
                     double *__restrict__ R, int32_t *__restrict__ flags, double atol, double rtol, double thr) {
-    __shared__ double red[8];
-    const int tid = threadIdx.x;
-    for (int64_t i = tid; i < r * r; i += blockDim.x) R[i] = ((i / r) == (i % r)) ? 1.0 : 0.0;
-    for (int64_t i = tid; i < r; i += blockDim.x) flags[i] = 0;
+    __shared__ double red[2][32];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
+    int par = 0;
+    // deterministic block sum: shuffle tree in the warp, warp partials added in warp order;
+    // the partial buffer alternates so one barrier per reduction suffices
+    auto bsum = [&](double v) -> double {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[par][warp] = v;
+        __syncthreads();
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += red[par][w];
+        par ^= 1;
+        return s;
+    };
+    for (int64_t i = tid; i < r * r; i += nthr) R[i] = ((i / r) == (i % r)) ? 1.0 : 0.0;
+    for (int64_t i = tid; i < r; i += nthr) flags[i] = 0;
     __syncthreads();
     for (int64_t i = offset; i < r; ++i) {
         double x[EPT];
         double ss = 0.0;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-            const int64_t c = tid + (int64_t)e * 256;
+            const int64_t c = tid + (int64_t)e * nthr;
             x[e] = c < k ? A[i * lda + c] : 0.0;
             ss = fma(x[e], x[e], ss);
         }
-        const double initial = sqrt(block_sum(ss, red));
+        const double initial = sqrt(bsum(ss));
         if (initial <= atol) {
             if (tid == 0) flags[i] = 1;
             __syncthreads();
@@ -99,27 +114,36 @@ gram_schmidt_kernel(double *__restrict__ A, int64_t r, int64_t k, int64_t lda, i
         bool removed = false;
         if (i > 0) {
             while (true) {
+                double aj[EPT], an[EPT];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int64_t c = tid + (int64_t)e * nthr;
+                    an[e] = c < k ? A[c] : 0.0;                     // row 0
+                }
                 for (int64_t j = 0; j < i; ++j) {
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) aj[e] = an[e];
+                    if (j + 1 < i) {
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) {
+                            const int64_t c = tid + (int64_t)e * nthr;
+                            an[e] = c < k ? A[(j + 1) * lda + c] : 0.0;
+                        }
+                    }
                     if (flags[j]) continue;
                     double d = 0.0;
 #pragma unroll
-                    for (int e = 0; e < EPT; ++e) {
-                        const int64_t c = tid + (int64_t)e * 256;
-                        if (c < k) d = fma(A[j * lda + c], x[e], d);
-                    }
-                    const double p = block_sum(d, red);
+                    for (int e = 0; e < EPT; ++e) d = fma(aj[e], x[e], d);
+                    const double p = bsum(d);
 #pragma unroll
-                    for (int e = 0; e < EPT; ++e) {
-                        const int64_t c = tid + (int64_t)e * 256;
-                        if (c < k) x[e] = fma(-p, A[j * lda + c], x[e]);
-                    }
+                    for (int e = 0; e < EPT; ++e) x[e] = fma(-p, aj[e], x[e]);
                     if (tid == 0) R[j * r + i] += p;
                 }
                 ss = 0.0;
 #pragma unroll
                 for (int e = 0; e < EPT; ++e) ss = fma(x[e], x[e], ss);
                 const double old = norm;
-                norm = sqrt(block_sum(ss, red));
+                norm = sqrt(bsum(ss));
                 if (norm <= rtol * initial) { removed = true; break; }
                 if (!(norm < thr * old)) break;
             }
@@ -130,7 +154,7 @@ gram_schmidt_kernel(double *__restrict__ A, int64_t r, int64_t k, int64_t lda, i
             const double inv = 1.0 / norm;
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
-                const int64_t c = tid + (int64_t)e * 256;
+                const int64_t c = tid + (int64_t)e * nthr;
                 if (c < k) A[i * lda + c] = x[e] * inv;
             }
             if (tid == 0) R[i * r + i] = norm;
@@ -272,11 +296,16 @@ extern "C" int rla_gram_schmidt_f64(double *a, int64_t r, int64_t k, int64_t lda
     if (r == 0) return RLA_OK;
     RLA_REQUIRE(a && R && flags, "rla_gram_schmidt_f64: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t ept = (k + 255) / 256;
-    if (ept <= 4) gram_schmidt_kernel<4><<<1, 256, 0, st>>>(a, r, k, lda, offset, R, flags, atol, rtol, thr);
-    else if (ept <= 16) gram_schmidt_kernel<16><<<1, 256, 0, st>>>(a, r, k, lda, offset, R, flags, atol, rtol, thr);
-    else if (ept <= 64) gram_schmidt_kernel<64><<<1, 256, 0, st>>>(a, r, k, lda, offset, R, flags, atol, rtol, thr);
-    else return fail(RLA_ERR_UNSUPPORTED, "rla_gram_schmidt_f64: sketch dimension k=%lld > 16384", (long long)k);
+    // about 8 elements per thread, at most 512 threads up to k = 8192 (registers hold the
+    // row, the current and the prefetched basis row), 1024 threads beyond
+    RLA_REQUIRE(k <= 16384, "rla_gram_schmidt_f64: sketch dimension k=%lld > 16384", (long long)k);
+    int threads = (int)(((k + 7) / 8 + 31) / 32 * 32);
+    threads = std::max(32, std::min(threads, k > 8192 ? 1024 : 512));
+    const int64_t ept = (k + threads - 1) / threads;
+    if (ept <= 4) gram_schmidt_kernel<4, 512><<<1, threads, 0, st>>>(a, r, k, lda, offset, R, flags, atol, rtol, thr);
+    else if (ept <= 8) gram_schmidt_kernel<8, 512><<<1, threads, 0, st>>>(a, r, k, lda, offset, R, flags, atol, rtol, thr);
+    else if (threads <= 512) gram_schmidt_kernel<16, 512><<<1, threads, 0, st>>>(a, r, k, lda, offset, R, flags, atol, rtol, thr);
+    else gram_schmidt_kernel<16, 1024><<<1, threads, 0, st>>>(a, r, k, lda, offset, R, flags, atol, rtol, thr);
     count_launch();
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;

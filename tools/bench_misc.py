@@ -19,7 +19,9 @@ for m, d in [(64, 24), (4096, 12), (1024, 16), (8, 27)]:
     print(f"fht_oop ({m}, 2^{d}) f64: {t:.3f} ms  {2 * a.numel() * 8 / t / 1e6:.0f} GB/s (read+write once)")
     del a
 U = torch.randn(256, 2 ** 23, dtype=torch.float64, device="cuda")
+from rla4mor_b200.rangefinder import sketch_block
 for kind in ("srht", "gauss"):
+    print(f"sketch only {kind}: {timeit(lambda: sketch_block(U, 2 ** 23, 1024, 0, kind)):.2f} ms")
     t = timeit(lambda: sketched_range_finder(U, 2 ** 23, 1024, 0, kind), 2)
     t0 = timeit(lambda: sketched_range_finder(U, 2 ** 23, 1024, 0, kind, svd=False), 2)
     print(f"range finder 2^23 x 256, k=1024, {kind}: sketch+GS+SVD {t:.1f} ms, sketch+GS {t0:.1f} ms")
