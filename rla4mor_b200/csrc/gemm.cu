@@ -386,7 +386,13 @@ struct GemmPlan {
 
 static GemmPlan plan_gemm(int64_t m, int64_t k, int64_t n) {
     GemmPlan p;
-    if (m > 64) { p.wm = 2; p.wn = 4; } else { p.wm = 1; p.wn = 8; }
+    // CTA tile (wm*64) x (wn*32).  128 x 128 measured best for m > 64 (256 x 64 halves the
+    // Theta generation per flop but is ~2% slower); 64 x 256 for m <= 64
+    static int wm_env = -1;
+    if (wm_env < 0) { const char *e = getenv("RLA_GEMM_WM"); wm_env = e ? atoi(e) : 0; }
+    if (wm_env == 1 || wm_env == 2 || wm_env == 4) p.wm = wm_env;
+    else p.wm = m > 64 ? 2 : 1;
+    p.wn = GWARPS / p.wm;
     p.bm = p.wm * 64; p.bn = p.wn * 32;
     p.mtiles = (int)((m + p.bm - 1) / p.bm);
     p.ntiles = (int)((k + p.bn - 1) / p.bn);
@@ -451,7 +457,10 @@ static int sketch_gemm(int mode, const double *theta, int64_t ldt, uint64_t seed
     a.ws = static_cast<double *>(ws); a.seed = seed; a.row0 = row0; a.col0 = col0;
     const int64_t grid = (int64_t)p.mtiles * p.ntiles * p.nchunks;
     RLA_REQUIRE(grid < (int64_t(1) << 31), "sketch gemm: grid too large");
-    if (p.wm == 2) {
+    if (p.wm == 4) {
+        rc = mode == 0 ? launch_gemm<4, 2, 0>(mu, mt, a, grid, st)
+           : mode == 1 ? launch_gemm<4, 2, 1>(mu, mt, a, grid, st) : launch_gemm<4, 2, 2>(mu, mt, a, grid, st);
+    } else if (p.wm == 2) {
         rc = mode == 0 ? launch_gemm<2, 4, 0>(mu, mt, a, grid, st)
            : mode == 1 ? launch_gemm<2, 4, 1>(mu, mt, a, grid, st) : launch_gemm<2, 4, 2>(mu, mt, a, grid, st);
     } else {
