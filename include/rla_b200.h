@@ -43,6 +43,11 @@ const char *rla_last_error(void);
  * the delta over its timed region as "gpu_launches") */
 unsigned long long rla_launch_count(void);
 
+/* Pitched host<->device copy on `stream` (cudaMemcpy2DAsync): used to stream column slabs
+ * of a row-major host block (pitches and width in BYTES; direction 0 = H2D, 1 = D2H). */
+int rla_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                     size_t height, int direction, void *stream);
+
 /* ------------------------------------------------------------------ SRHT ---
  * Replaces srht(x, k, seed, nthreads)            rla/srht.py:136-177
  * as called by SrhtEmbedding.apply               rla/embeddings.py:167-172.

@@ -33,3 +33,16 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n
 extern "C" int rla_version(void) { return 100; }
 extern "C" unsigned long long rla_launch_count(void) { return __atomic_load_n(&rla::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char *rla_last_error(void) { return rla::g_err; }
+
+// Pitched copy between host and device (cudaMemcpy2DAsync): the column slabs of a
+// row-major host block that streaming.py pipelines to the GPU.  direction 0: H2D, 1: D2H.
+extern "C" int rla_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                                size_t height, int direction, void *stream) {
+    RLA_REQUIRE(dst && src, "rla_copy2d_async: null pointer");
+    RLA_REQUIRE(direction == 0 || direction == 1, "rla_copy2d_async: direction must be 0 (H2D) or 1 (D2H)");
+    if (width_bytes == 0 || height == 0) return RLA_OK;
+    RLA_CUDA_CHECK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
+                                     direction == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                     (cudaStream_t)stream));
+    return RLA_OK;
+}

@@ -83,6 +83,16 @@ def _wrap_result(kind, space, t):
     return t
 
 
+def _is_host_tensor(U):
+    """A CPU torch tensor: a block that lives in (ideally pinned) host memory and is streamed
+    to the GPU in pieces instead of being copied whole."""
+    try:
+        import torch
+    except ImportError:
+        return False
+    return isinstance(U, torch.Tensor) and not U.is_cuda and U.dim() == 2
+
+
 def _unwrap(U):
     """-> (CUDA tensor (len, dim), kind)"""
     if isinstance(U, DeviceVectorArray):
@@ -272,6 +282,12 @@ class SrhtEmbedding(RandomEmbedding):
 
     def apply(self, U, mu=None):                                           # :167-172
         torch = require_cuda()
+        if _is_host_tensor(U) and isinstance(self.sqrt_product, IdentityOperator):
+            # block in host memory: vectors are independent, stream them in groups; the
+            # sketch comes back as a pinned host tensor
+            from .streaming import apply_streamed
+            assert U.shape[1] == self.source.dim
+            return apply_streamed(self.apply, U, self.range.dim, return_host=True)
         qu, kind = self._apply_sqrt_product(U)
         if qu.is_complex():
             m = qu.shape[0]
@@ -373,8 +389,16 @@ class GaussianEmbedding(RandomEmbedding):
 
     def apply(self, U, mu=None):                                           # :250-254
         torch = require_cuda()
-        qu, kind = self._apply_sqrt_product(U)
         k = self.range.dim
+        if _is_host_tensor(U) and isinstance(self.sqrt_product, IdentityOperator):
+            # block in host memory: streamed by column slabs (on-the-fly Theta: accumulate per
+            # slab at full GEMM height) or by groups of vectors (explicit Theta)
+            from .streaming import apply_streamed, apply_streamed_rng
+            assert U.shape[1] == self.source.dim
+            if self._rng_mode == "mt19937" or U.dtype != torch.float64:
+                return apply_streamed(self.apply, U, k, return_host=True)
+            return apply_streamed_rng(self._seed, self._kind(), 1.0 / np.sqrt(k), k, U, return_host=True)
+        qu, kind = self._apply_sqrt_product(U)
         if qu.dtype != torch.float64:
             assert not qu.is_complex(), "complex blocks: sketch real and imaginary parts separately"
             qu = qu.to(torch.float64)

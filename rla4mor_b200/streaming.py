@@ -10,7 +10,7 @@ independent, so no result depends on the grouping.
 import numpy as np
 import torch
 
-from ._lib import require_cuda
+from ._lib import check, lib, require_cuda
 
 
 def pinned_like(shape, dtype=torch.float64):
@@ -56,3 +56,57 @@ def apply_streamed(apply_fn, U_host, k, rows_per_chunk=None, out=None, device=No
         main.synchronize()
         return host
     return out
+
+
+def apply_streamed_rng(seed, kind, scale, k, U_host, cols_per_slab=None, device=None, return_host=False):
+    """On-the-fly (Philox) dense sketch of a HOST block, streamed by COLUMN slabs of the
+    vector dimension: slab j is copied host->device with a pitched copy while slab j-1 is
+    sketched against Theta[:, slab] (column offset into the virtual matrix) and accumulated
+    into the (m, k) result.  Unlike row chunks this keeps the GEMM at full height (every
+    Theta entry is still generated once per 128 vectors) -- a block of m vectors costs the
+    same k*n generated entries however it is cut along n."""
+    from . import dense
+    require_cuda()
+    if isinstance(U_host, np.ndarray):
+        U_host = torch.from_numpy(np.ascontiguousarray(U_host))
+    assert not U_host.is_cuda and U_host.dim() == 2 and U_host.dtype == torch.float64
+    assert U_host.stride(1) == 1
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    m, n = U_host.shape
+    out = torch.zeros((m, k), dtype=torch.float64, device=device)
+    if m == 0 or n == 0:
+        return out
+    if cols_per_slab is None:
+        cols_per_slab = max(4096, ((1 << 30) // (8 * m)) // 4096 * 4096)          # ~1 GiB per slab
+    cols_per_slab = max(16, (min(cols_per_slab, n) + 15) // 16 * 16)
+    main = torch.cuda.current_stream(device)
+    copy = torch.cuda.Stream(device)
+    bufs = [torch.empty((m, cols_per_slab), dtype=torch.float64, device=device) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    spitch = U_host.stride(0) * 8
+    src0 = U_host.data_ptr()
+    slabs = [(c, min(c + cols_per_slab, n)) for c in range(0, n, cols_per_slab)]
+    with torch.cuda.device(device):
+        for i, (c0, c1) in enumerate(slabs):
+            b = i & 1
+            w = c1 - c0
+            if i >= 2:
+                copy.wait_event(consumed[b])
+            check(lib().rla_copy2d_async(bufs[b].data_ptr(), cols_per_slab * 8, src0 + c0 * 8, spitch, w * 8, m, 0,
+                                         ctypes_stream(copy)), "rla_copy2d_async")
+            copied[b].record(copy)
+            main.wait_event(copied[b])
+            dense.embed_apply_rng(seed, kind, scale, k, bufs[b][:, :w], col0=c0, out=out, accumulate=(i > 0))
+            consumed[b].record(main)
+    if return_host:
+        host = torch.empty((m, k), dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        main.synchronize()
+        return host
+    return out
+
+
+def ctypes_stream(stream):
+    import ctypes
+    return ctypes.c_void_p(stream.cuda_stream)

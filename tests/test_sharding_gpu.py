@@ -74,3 +74,21 @@ def test_streaming_host_block():
     assert not y.is_cuda and rel_fro(y.numpy(), oracle.srht(x, k, seed=2)) < 1e-12
     y2 = apply_streamed(emb.apply, x, k, rows_per_chunk=5)
     assert y2.is_cuda and rel_fro(y2.cpu().numpy(), oracle.srht(x, k, seed=2)) < 1e-12
+
+
+def test_embedding_apply_on_host_blocks():
+    import rla4mor_b200 as rb
+    from oracle import embeddings_oracle as eo
+    n, k = 9000, 64
+    x = np.random.RandomState(2).standard_normal((21, n))
+    host = torch.from_numpy(x).pin_memory()
+    g = rb.GaussianEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k, "rng": "philox"}, _seed=4)
+    y = g.apply(host)                                   # column-slab streaming, result on the host
+    assert not y.is_cuda and rel_fro(y.numpy(), eo.gaussian_apply(x, g.get_random_matrix())) < 1e-12
+    from rla4mor_b200.streaming import apply_streamed_rng
+    y2 = apply_streamed_rng(4, 0, 1.0 / np.sqrt(k), k, host, cols_per_slab=2048)      # several slabs
+    assert rel_fro(y2.cpu().numpy(), y.numpy()) < 1e-13
+    e = rb.GaussianEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k}, _seed=4)
+    assert rel_fro(e.apply(host).numpy(), eo.gaussian_apply(x, eo.gaussian_random_matrix(k, n, 4))) < 1e-12
+    s = rb.SrhtEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k}, _seed=4)
+    assert rel_fro(s.apply(host).numpy(), oracle.srht(x, k, seed=4)) < 1e-12
