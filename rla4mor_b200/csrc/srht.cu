@@ -12,14 +12,15 @@
 // collapse, for the k sampled outputs only, into one signed gather-accumulate per
 // (sample, tile).  x is read from HBM exactly once and never written.
 //
-// Work decomposition: CTA = 128 threads = two 64-thread groups, one tile per
-// group per iteration; each CTA owns a power-of-two chunk of consecutive tiles
-// of ONE vector (row of x) and keeps NSLOT sample accumulators per thread in
-// registers.  Tiles are visited in Gray-code order so the per-sample sign
-// (-1)^popcount(sh & jh) is maintained by one conditional sign flip of the
-// accumulator per step (integer XOR, no popcount, no FP64 op).  Per-chunk partial
-// sketches go to a workspace and are summed in chunk order by a small finalize
-// kernel (deterministic, no atomics).
+// Work decomposition: a CTA owns a power-of-two chunk of consecutive tiles of ONE vector (row
+// of x) and keeps the sample accumulators in registers.  Tiles are visited in Gray-code
+// order so the per-sample sign (-1)^popcount(sh & jh) is maintained by one conditional sign
+// flip of the accumulator per step (integer XOR, no popcount, no FP64 op).  Per-chunk partial
+// sketches go to a workspace and are summed in chunk order by a small finalize kernel
+// (deterministic, no atomics).  Two kernels share this scheme:
+//   srht_ws_kernel   (default) warp-specialised: four 64-thread transform groups that hold
+//                    only tile data + four gather warps that hold the accumulators;
+//   srht_main_kernel single-role 128-thread CTAs for problems of a few tiles per SM.
 #include "tile.cuh"
 #include <algorithm>
 #include <new>
@@ -43,7 +44,12 @@ struct SrhtArgs {
     int64_t ntiles_valid;    // tiles that contain at least one element < n
 };
 
-template <typename T, int NSLOT, bool PF>
+// ---------------------------------------------------------------------------
+// Single-role variant for small problems (a few tiles per SM): 128-thread CTAs, two per SM;
+// every thread transforms AND accumulates, tile pairs are processed in lockstep.  Short
+// prologue, no idle gather warps; register-bound (64 data + NSLOT accumulator doubles), so
+// loads do not overlap the transform -- the warp-specialised kernel below is the fast path.
+template <typename T, int NSLOT>
 __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
@@ -54,8 +60,7 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
     const int npairs = 1 << (a.log2L - 1);
     const T *rowp = a.x + row * a.ldx;
     T *buf = sm + grp * TILE;
-    // sample descriptors of this thread live in shared memory (behind the two tile
-    // buffers) so the gather never queues behind in-flight tile loads
+    // sample descriptors of this thread live in shared memory behind the two tile buffers
     uint32_t *sdesc = reinterpret_cast<uint32_t *>(sm + 2 * TILE) + tid;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) sdesc[s * CTA] = __ldg(a.desc + s * CTA + tid);
@@ -63,30 +68,20 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
     T acc[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) acc[s] = T(0);
-
-    // tile of this group in pair u (Gray-code order); valid tiles form a prefix
-    auto tile_of = [&](int u) -> int64_t { return c0 + 2 * (int64_t)(u ^ (u >> 1)) + grp; };
     auto is_fast = [&](int64_t jh) -> bool { return a.aligned && (jh + 1) * (int64_t)TILE <= a.n; };
 
-    T v[64];
-    uint64_t sw = 0;
-    if (PF) {   // prologue: loads of pair 0
-        const int64_t jh = tile_of(0);
-        if (jh < a.ntiles_valid) {
-            sw = __ldg(a.signw + jh * GROUP + tg);
-            if (is_fast(jh)) load_tile_fast(v, rowp + jh * TILE, tg);
-        }
-    }
     for (int u = 0; u < npairs; ++u) {
+        // tile pair u in Gray-code order; valid tiles form a prefix
         const int64_t jhA = c0 + 2 * (int64_t)(u ^ (u >> 1));
         const int64_t jh = jhA + grp;
         // sign flip when moving from pair u-1 to pair u: bit (ctz(u)+1) of sh = desc bit 13+ctz(u)
         const int fl_shift = 31 - (13 + (u ? __ffs(u) - 1 : 0));
         if (jhA < a.ntiles_valid) {
+            T v[64];
             if (jh < a.ntiles_valid) {
-                if (!PF) sw = __ldg(a.signw + jh * GROUP + tg);
-                if (!is_fast(jh)) load_tile_slow(v, rowp, a.n, jh, tg, buf, grp);
-                else if (!PF) load_tile_fast(v, rowp + jh * TILE, tg);
+                const uint64_t sw = __ldg(a.signw + jh * GROUP + tg);
+                if (is_fast(jh)) load_tile_fast(v, rowp + jh * TILE, tg);
+                else load_tile_slow(v, rowp, a.n, jh, tg, buf, grp);
                 flip_signs(v, sw);
             } else {
 #pragma unroll
@@ -94,15 +89,6 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
             }
             tile_fwht(v, buf, tg, grp);
             __syncthreads();
-            // v is dead and its write-back is ordered before the barrier: start the loads
-            // of the next pair now so they fly during the gather
-            if (PF && u + 1 < npairs) {
-                const int64_t jn = tile_of(u + 1);
-                if (jn < a.ntiles_valid) {
-                    sw = __ldg(a.signw + jn * GROUP + tg);
-                    if (is_fast(jn)) load_tile_fast(v, rowp + jn * TILE, tg);
-                }
-            }
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
                 const uint32_t dsc = sdesc[s * CTA];
@@ -114,10 +100,7 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
             __syncthreads();
         } else {
 #pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
-                const uint32_t dsc = sdesc[s * CTA];
-                acc[s] = xor_sign(acc[s], dsc << fl_shift);
-            }
+            for (int s = 0; s < NSLOT; ++s) acc[s] = xor_sign(acc[s], sdesc[s * CTA] << fl_shift);
         }
     }
     // accumulators are relative to the sign of the last A tile: undo it
@@ -134,17 +117,18 @@ __global__ void __launch_bounds__(CTA, 2) srht_main_kernel(const SrhtArgs<T> a) 
 
 // ---------------------------------------------------------------------------
 // Warp-specialised variant (default): one CTA of 384 threads per SM.
-//   threads   0..255  four independent 64-thread transform groups; group q owns tile buffer q
+//   threads   0..127  gather warps: own the NSLOT sample accumulators (and their descriptors)
+//                     in registers, serve the four tile buffers in tile order
+//   threads 128..383  four independent 64-thread transform groups; group q owns tile buffer q
 //                     and the tiles t = q, q+4, q+8, ... of the CTA's Gray-code tile sequence
-//   threads 256..383  gather warps: own the NSLOT sample accumulators, serve the four
-//                     buffers in tile order
 // A transform thread holds only its 64 tile elements (no accumulators), so the loads of its
 // next tile are issued right behind the write-back stores of the current one and fly while
 // the gather warps read it.  The four groups drift freely (each meets only the gather warps,
 // through two named barriers per group: A_q "tile ready", B_q "buffer free"), so one group's
 // FP64 butterflies overlap another's shared-memory passes and a third's load latency.
-// setmaxnreg moves registers from the gather warps (104) to the transform warps (200);
-// 256*200 + 128*104 = 384*168, the launch allocation.
+// setmaxnreg rebalances the launch allocation (384 x 168 registers): transform warps 184,
+// gather warps 136 (32 accumulators + 32 sample descriptors in registers);
+// 256*184 + 128*136 = 384*168.
 constexpr int WS_THREADS = 3 * CTA;
 constexpr int WS_GROUPS = 4;
 
@@ -159,16 +143,18 @@ template <typename T, int NSLOT>
 __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);                 // 4 tile buffers
-    const int tid = threadIdx.x;
+    // warps 0..3 gather, warps 4..11 transform: the issue arbiter favours high warp ids, and
+    // the transform warps are the critical path
+    const int tid = threadIdx.x - CTA;
     const int64_t row = blockIdx.x / a.nchunks;
     const int64_t chunk = blockIdx.x % a.nchunks;
     const int64_t c0 = chunk << a.log2L;
     const int ntl = 1 << a.log2L;                            // tiles of this CTA
     // barrier ids: 1..4 group-internal (64), 5..8 A_q, 9..12 B_q (64 + 128 = 192 threads)
 
-    if (tid < 2 * CTA) {
+    if (tid >= 0) {
         // ------------------------------------------------------------ transform warps
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
         const int q = tid >> 6, tg = tid & 63;
         const T *rowp = a.x + row * a.ldx;
         T *buf = sm + q * TILE;
@@ -254,11 +240,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
     }
 
     // ------------------------------------------------------------------ gather warps
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    const int gt = tid - 2 * CTA;
-    uint32_t *sdesc = reinterpret_cast<uint32_t *>(sm + WS_GROUPS * TILE) + gt;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+    const int gt = threadIdx.x;
+    // sample descriptors and accumulators of this thread both live in registers
+    uint32_t dsc[NSLOT];
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) sdesc[s * CTA] = __ldg(a.desc + s * CTA + gt);
+    for (int s = 0; s < NSLOT; ++s) dsc[s] = __ldg(a.desc + s * CTA + gt);
     T acc[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) acc[s] = T(0);
@@ -271,13 +258,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
         if (jh < a.ntiles_valid) {
             const T *tb = sm + q * TILE;
 #pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
-                const uint32_t dsc = sdesc[s * CTA];
-                acc[s] = xor_sign(acc[s], dsc << fl_shift) + tb[dsc & (TILE - 1)];
-            }
+            for (int s = 0; s < NSLOT; ++s)
+                acc[s] = xor_sign(acc[s], dsc[s] << fl_shift) + tb[dsc[s] & (TILE - 1)];
         } else {
 #pragma unroll
-            for (int s = 0; s < NSLOT; ++s) acc[s] = xor_sign(acc[s], sdesc[s * CTA] << fl_shift);
+            for (int s = 0; s < NSLOT; ++s) acc[s] = xor_sign(acc[s], dsc[s] << fl_shift);
         }
         if (t + WS_GROUPS < ntl) bar_arrive(9 + q, 192);               // somebody will wait for it
     }
@@ -286,8 +271,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
     T *wsp = a.ws + ((chunk * a.m + row) * (int64_t)(NSLOT * CTA));
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
-        const uint32_t dsc = sdesc[s * CTA];
-        const uint32_t par = __popc((dsc >> TILE_LOG2) & jlast) & 1u;
+        const uint32_t par = __popc((dsc[s] >> TILE_LOG2) & jlast) & 1u;
         wsp[s * CTA + gt] = xor_sign(acc[s], par << 31);
     }
 }
@@ -312,21 +296,76 @@ __global__ void srht_finalize_kernel(const T *__restrict__ ws, const int32_t *__
 
 using namespace rla;
 
+// One assignment of the distinct samples to (pass, slot, thread) cells plus the map from
+// sample index to cell.  A plan carries two: the smallest power-of-two slot count that fits
+// (single-role kernel, registers are scarce there) and 32 slots (warp-specialised kernel:
+// measured fastest for every k, half-empty slots included -- more slack per bank bucket
+// means no overflow samples and no bank conflicts in the gather).
+struct SrhtDescSet {
+    int nslot = 0;
+    size_t off_desc = 0, off_slot = 0;
+};
+
 struct rla_srht_plan {
     int64_t n = 0, k = 0;
     int d = 0;
     int elem_bytes = 8;
     int64_t ntiles = 0;        // padded tiles per row (>= 2)
     int64_t ntiles_valid = 0;
-    int nslot = 0;             // accumulators per thread (4, 8, 16 or 32)
     int npass = 1;
     int64_t nuniq = 0;
-    size_t off_sign = 0, off_desc = 0, off_slot = 0;
+    size_t off_sign = 0;
+    SrhtDescSet sets[2];       // [0] minimal slot count, [1] 32 slots
     std::vector<unsigned char> image;
     const unsigned char *dev = nullptr;
 };
 
 static size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+// slot assignment: lane (tid % lanes) should equal the bank group of the gathered word
+static void build_desc_set(rla_srht_plan *p, const SrhtDescSet &set, const std::vector<int64_t> &uniq,
+                           const int64_t *idx, int64_t per_pass) {
+    const int mask = p->elem_bytes == 8 ? 15 : 31;
+    const int lanes = mask + 1;                // lanes per shared-memory wavefront
+    const int nst = set.nslot * CTA;
+    uint32_t *desc = reinterpret_cast<uint32_t *>(p->image.data() + set.off_desc);
+    std::vector<int32_t> slot_of_uniq(uniq.size());
+    const int threads_per_bucket = CTA / lanes;
+    for (int pass = 0; pass < p->npass; ++pass) {
+        const int64_t u0 = pass * per_pass, u1 = std::min<int64_t>(p->nuniq, u0 + per_pass);
+        std::vector<int> cnt(lanes, 0);
+        std::vector<char> used(nst, 0);
+        std::vector<int64_t> overflow;
+        const int cap = set.nslot * threads_per_bucket;
+        for (int64_t u = u0; u < u1; ++u) {
+            const int pos = tile_pos((int)(uniq[u] & (TILE - 1)), mask);
+            const int b = pos & mask;
+            if (cnt[b] < cap) {
+                const int c = cnt[b]++;
+                const int tid = b + lanes * (c % threads_per_bucket), s = c / threads_per_bucket;
+                const int cell = s * CTA + tid;
+                used[cell] = 1;
+                desc[(size_t)pass * nst + cell] = (uint32_t)pos | ((uint32_t)(uniq[u] >> TILE_LOG2) << TILE_LOG2);
+                slot_of_uniq[u] = pass * nst + cell;
+            } else {
+                overflow.push_back(u);
+            }
+        }
+        int cell = 0;
+        for (int64_t u : overflow) {           // bucket full: any free cell (costs a bank conflict)
+            while (used[cell]) ++cell;
+            used[cell] = 1;
+            const int pos = tile_pos((int)(uniq[u] & (TILE - 1)), mask);
+            desc[(size_t)pass * nst + cell] = (uint32_t)pos | ((uint32_t)(uniq[u] >> TILE_LOG2) << TILE_LOG2);
+            slot_of_uniq[u] = pass * nst + cell;
+        }
+    }
+    int32_t *slotmap = reinterpret_cast<int32_t *>(p->image.data() + set.off_slot);
+    for (int64_t i = 0; i < p->k; ++i) {
+        const size_t u = std::lower_bound(uniq.begin(), uniq.end(), idx[i]) - uniq.begin();
+        slotmap[i] = slot_of_uniq[u];
+    }
+}
 
 extern "C" int rla_srht_plan_create(rla_srht_plan **out, const int8_t *signs, int64_t n,
                                     const int64_t *idx, int64_t k, int elem_bytes) {
@@ -345,8 +384,6 @@ extern "C" int rla_srht_plan_create(rla_srht_plan **out, const int8_t *signs, in
     const int dp = std::max(d, TILE_LOG2 + 1);
     p->ntiles = int64_t(1) << (dp - TILE_LOG2);
     p->ntiles_valid = (n + TILE - 1) / TILE;
-    const int mask = elem_bytes == 8 ? 15 : 31;
-    const int lanes = mask + 1;                // lanes per shared-memory wavefront
     // distinct sample values
     std::vector<int64_t> uniq(idx, idx + k);
     std::sort(uniq.begin(), uniq.end());
@@ -356,12 +393,17 @@ extern "C" int rla_srht_plan_create(rla_srht_plan **out, const int8_t *signs, in
     const int64_t per_pass = (p->nuniq + p->npass - 1) / p->npass;
     int nslot = 4;
     while ((int64_t)nslot * CTA < per_pass) nslot *= 2;
-    p->nslot = nslot;
-    const int nst = nslot * CTA;
+    p->sets[0].nslot = nslot;
+    p->sets[1].nslot = MAX_NSLOT;
+    const size_t slot_bytes = align16((size_t)std::max<int64_t>(k, 1) * 4);
     p->off_sign = 0;
-    p->off_desc = align16(p->off_sign + (size_t)p->ntiles_valid * GROUP * 8);
-    p->off_slot = align16(p->off_desc + (size_t)p->npass * nst * 4);
-    p->image.assign(align16(p->off_slot + (size_t)std::max<int64_t>(k, 1) * 4), 0);
+    size_t off = align16(p->off_sign + (size_t)p->ntiles_valid * GROUP * 8);
+    for (SrhtDescSet &set : p->sets) {
+        set.off_desc = off;
+        set.off_slot = align16(off + (size_t)p->npass * set.nslot * CTA * 4);
+        off = set.off_slot + slot_bytes;
+    }
+    p->image.assign(off, 0);
     // packed sign bits: word [jh*64 + tg], bit rho=2h+l <-> element jh*4096 + 128h + 2tg + l
     uint64_t *sw = reinterpret_cast<uint64_t *>(p->image.data() + p->off_sign);
     for (int64_t j = 0; j < n; ++j) {
@@ -372,44 +414,7 @@ extern "C" int rla_srht_plan_create(rla_srht_plan **out, const int8_t *signs, in
             sw[jh * GROUP + tg] |= uint64_t(1) << (2 * h + l);
         }
     }
-    // slot assignment: lane (tid % lanes) should equal the bank group of the gathered word
-    uint32_t *desc = reinterpret_cast<uint32_t *>(p->image.data() + p->off_desc);
-    std::vector<int32_t> slot_of_uniq(uniq.size());
-    const int threads_per_bucket = CTA / lanes;
-    for (int pass = 0; pass < p->npass; ++pass) {
-        const int64_t u0 = pass * per_pass, u1 = std::min<int64_t>(p->nuniq, u0 + per_pass);
-        std::vector<int> cnt(lanes, 0);
-        std::vector<char> used(nst, 0);
-        std::vector<int64_t> overflow;
-        const int cap = nslot * threads_per_bucket;
-        for (int64_t u = u0; u < u1; ++u) {
-            const int pos = tile_pos((int)(uniq[u] & (TILE - 1)), mask);
-            const int b = pos & mask;
-            if (cnt[b] < cap) {
-                const int c = cnt[b]++;
-                const int tid = b + lanes * (c % threads_per_bucket), s = c / threads_per_bucket;
-                const int cell = s * CTA + tid;
-                used[cell] = 1;
-                desc[(size_t)pass * nst + cell] = (uint32_t)pos | ((uint32_t)(uniq[u] >> TILE_LOG2) << TILE_LOG2);
-                slot_of_uniq[u] = pass * nst + cell;
-            } else {
-                overflow.push_back(u);
-            }
-        }
-        int cell = 0;
-        for (int64_t u : overflow) {
-            while (used[cell]) ++cell;
-            used[cell] = 1;
-            const int pos = tile_pos((int)(uniq[u] & (TILE - 1)), mask);
-            desc[(size_t)pass * nst + cell] = (uint32_t)pos | ((uint32_t)(uniq[u] >> TILE_LOG2) << TILE_LOG2);
-            slot_of_uniq[u] = pass * nst + cell;
-        }
-    }
-    int32_t *slotmap = reinterpret_cast<int32_t *>(p->image.data() + p->off_slot);
-    for (int64_t i = 0; i < k; ++i) {
-        const size_t u = std::lower_bound(uniq.begin(), uniq.end(), idx[i]) - uniq.begin();
-        slotmap[i] = slot_of_uniq[u];
-    }
+    for (const SrhtDescSet &set : p->sets) build_desc_set(p, set, uniq, idx, per_pass);
     *out = p;
     return RLA_OK;
 }
@@ -461,32 +466,12 @@ extern "C" size_t rla_srht_workspace_bytes(const rla_srht_plan *p, int64_t m) {
     // the chunk count depends on m only through choose_log2L; take the max over the two
     // extreme choices so that a forced/tuned L never overflows the buffer
     const int64_t nch = valid_chunks(p, choose_log2L(p, m));
-    return (size_t)p->npass * nch * m * p->nslot * CTA * p->elem_bytes;
-}
-
-static bool use_prefetch() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("RLA_SRHT_PREFETCH");
-        v = e ? atoi(e) : 0;
-    }
-    return v != 0;
-}
-
-template <typename T, int NSLOT, bool PF>
-static int launch_main_pf(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
-    auto kern = srht_main_kernel<T, NSLOT, PF>;
-    const int smem = 2 * TILE * sizeof(T) + NSLOT * CTA * 4;
-    RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(unsigned)grid, CTA, smem, st>>>(a);
-    count_launch();
-    RLA_CUDA_CHECK(cudaGetLastError());
-    return RLA_OK;
+    return (size_t)p->npass * nch * m * MAX_NSLOT * CTA * p->elem_bytes;      // the larger of the two descriptor sets
 }
 
 // 0: warp-specialised 384-thread CTAs, one per SM (default);
 // 1: single-role 128-thread CTAs, two per SM: shorter prologue, better for tiny problems
-//    (a few tiles per SM), where launch and drain dominate
+//    (a few tiles per SM), where launch and drain dominate.  RLA_SRHT_VARIANT overrides.
 static int srht_variant_for(int64_t total_tiles) {
     static int v = -2;
     if (v == -2) {
@@ -498,21 +483,21 @@ static int srht_variant_for(int64_t total_tiles) {
 }
 
 template <typename T, int NSLOT>
-static int launch_ws(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
-    auto kern = srht_ws_kernel<T, NSLOT>;
-    const int smem = 4 * TILE * sizeof(T) + NSLOT * CTA * 4;
-    RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(unsigned)grid, WS_THREADS, smem, st>>>(a);
+static int launch_main(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
+    if (srht_variant_for(a.m * a.ntiles_valid) == 0) {
+        auto kern = srht_ws_kernel<T, NSLOT>;
+        const int smem = WS_GROUPS * TILE * sizeof(T);
+        RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(unsigned)grid, WS_THREADS, smem, st>>>(a);
+    } else {
+        auto kern = srht_main_kernel<T, NSLOT>;
+        const int smem = 2 * TILE * sizeof(T) + NSLOT * CTA * 4;
+        RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(unsigned)grid, CTA, smem, st>>>(a);
+    }
     count_launch();
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;
-}
-
-template <typename T, int NSLOT>
-static int launch_main(const SrhtArgs<T> &a, int64_t grid, cudaStream_t st) {
-    if (srht_variant_for(a.m * a.ntiles_valid) == 0) return launch_ws<T, NSLOT>(a, grid, st);
-    return use_prefetch() ? launch_main_pf<T, NSLOT, true>(a, grid, st)
-                          : launch_main_pf<T, NSLOT, false>(a, grid, st);
 }
 
 template <typename T>
@@ -537,7 +522,9 @@ static int srht_apply(const rla_srht_plan *p, const T *x, int64_t m, int64_t ldx
     cudaStream_t st = (cudaStream_t)stream;
     const int log2L = choose_log2L(p, m);
     const int64_t nch = valid_chunks(p, log2L);
-    const int nst = p->nslot * CTA;
+    const int variant = srht_variant_for(m * p->ntiles_valid);
+    const SrhtDescSet &set = p->sets[variant == 0 ? 1 : 0];
+    const int nst = set.nslot * CTA;
     const size_t need = (size_t)p->npass * nch * m * nst * sizeof(T);
     if (ws_bytes < need) return fail(RLA_ERR_WORKSPACE, "rla_srht_apply: workspace %zu < %zu bytes", ws_bytes, need);
     const int64_t grid = m * nch;
@@ -547,10 +534,10 @@ static int srht_apply(const rla_srht_plan *p, const T *x, int64_t m, int64_t ldx
         SrhtArgs<T> a;
         a.x = x; a.ldx = ldx; a.n = p->n; a.m = m;
         a.signw = reinterpret_cast<const uint64_t *>(p->dev + p->off_sign);
-        a.desc = reinterpret_cast<const uint32_t *>(p->dev + p->off_desc) + (size_t)pass * nst;
+        a.desc = reinterpret_cast<const uint32_t *>(p->dev + set.off_desc) + (size_t)pass * nst;
         a.ws = static_cast<T *>(ws) + (size_t)pass * nch * m * nst;
         a.log2L = log2L; a.nchunks = nch; a.ntiles_valid = p->ntiles_valid; a.aligned = vec ? 1 : 0;
-        int rc = dispatch_nslot<T>(p->nslot, a, grid, st);
+        int rc = dispatch_nslot<T>(set.nslot, a, grid, st);
         if (rc != RLA_OK) return rc;
     }
     const int fin_threads = 256;
@@ -560,7 +547,7 @@ static int srht_apply(const rla_srht_plan *p, const T *x, int64_t m, int64_t ldx
         const int64_t rows = std::min<int64_t>(65535, m - r0);
         fgrid.y = (unsigned)rows;
         srht_finalize_kernel<T><<<fgrid, fin_threads, 0, st>>>(
-            static_cast<const T *>(ws) + r0 * nst, reinterpret_cast<const int32_t *>(p->dev + p->off_slot),
+            static_cast<const T *>(ws) + r0 * nst, reinterpret_cast<const int32_t *>(p->dev + set.off_slot),
             y + r0 * ldy, ldy, p->k, m, nch, nst, (int64_t)nch * m * nst, scale);
         count_launch();
     }
