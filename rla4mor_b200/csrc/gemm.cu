@@ -69,6 +69,9 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double2 &v) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+}
 // 4 consecutive doubles k = 4t..4t+3 of row `row` of a [rows][16] box stored with the
 // 128-byte TMA swizzle (16-byte chunk index XOR (row & 7))
 __device__ __forceinline__ void lds_row4(const double *tile, int row, int t, double (&v)[4]) {
@@ -198,18 +201,17 @@ sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
     // a thread owns k = 4t + 2h + {0, 1} of every row: the 16-byte chunk 2t + h, XOR-swizzled
     // with (row & 7) = g for every row this thread touches.
     double2 a8[2][8], b8[2][4];
+    const uint32_t smem_base = smem_u32(smem);
     const uint32_t row_off = (uint32_t)g * 128u;
     const uint32_t off0 = row_off + ((uint32_t)((2 * t) ^ g) << 4);
     const uint32_t off1 = row_off + ((uint32_t)((2 * t + 1) ^ g) << 4);
     const uint32_t a_warp = (uint32_t)(wm * 64) * 128u, b_warp = (uint32_t)A_BYTES + (uint32_t)(wn * 32) * 128u;
 #define LOAD_FRAGS(BUF, STAGE, OFF)                                                              \
     {                                                                                            \
-        const unsigned char *sa_ = smem + (STAGE) * STAGE_BYTES + a_warp + (OFF);                \
-        const unsigned char *sb_ = smem + (STAGE) * STAGE_BYTES + b_warp + (OFF);                \
-        _Pragma("unroll") for (int i = 0; i < 8; ++i)                                            \
-            a8[BUF][i] = *reinterpret_cast<const double2 *>(sa_ + i * 1024);                     \
-        _Pragma("unroll") for (int j = 0; j < 4; ++j)                                            \
-            b8[BUF][j] = *reinterpret_cast<const double2 *>(sb_ + j * 1024);                     \
+        const uint32_t sa_ = smem_base + (STAGE) * STAGE_BYTES + a_warp + (OFF);                 \
+        const uint32_t sb_ = smem_base + (STAGE) * STAGE_BYTES + b_warp + (OFF);                 \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) lds_f64x2(sa_ + i * 1024, a8[BUF][i]);     \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) lds_f64x2(sb_ + j * 1024, b8[BUF][j]);     \
     }
 #define MMA_HALF(BUF, PRED)                                                                      \
     {                                                                                            \
