@@ -62,61 +62,80 @@ __device__ __forceinline__ void butterflies64_masked(T (&v)[64], int mask) {
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(CTA, 2) fwht_pass_kernel(const T *__restrict__ in, int64_t ldi,
-                                                            T *__restrict__ out, int64_t ldo,
-                                                            FwhtPass p, int64_t ntiles, T post_scale, int vec) {
+// One pass: persistent 64-thread CTAs (one tile group each, four per SM), each looping over
+// tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The loop is rotated so that there is ONE
+// load site: the stores of tile t (read back from shared memory in the coalesced round-1
+// layout) are interleaved, pair by pair, with the loads of the CTA's next tile into the
+// registers they free, so the next tile's HBM latency overlaps this tile's stores and the
+// other CTAs' butterflies.
+// CONTIG: every tile is 4096 contiguous, 16-byte aligned elements of one row (first pass of
+// rows of length >= 4096): the index arithmetic of fwht_map disappears.
+template <typename T, bool CONTIG>
+__global__ void __launch_bounds__(GROUP, 4) fwht_pass_kernel(const T *__restrict__ in, int64_t ldi,
+                                                             T *__restrict__ out, int64_t ldo,
+                                                             FwhtPass p, int64_t ntiles, T post_scale, int vec) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
+    T *buf = reinterpret_cast<T *>(smem_raw);
     constexpr int M = Elem<T>::MASK;
-    const int tid = threadIdx.x, grp = tid >> 6;
-    int tg = tid & 63;
-    const int64_t t = (int64_t)blockIdx.x * 2 + grp;
-    if (t >= ntiles) return;                       // whole group leaves: only group barriers below
-    T *buf = sm + grp * TILE;
+    int tg = threadIdx.x;
     // stage mask over tile bits -> register-bit masks of the two rounds
     const int smask = ((1 << p.nb) - 1) << p.cbits;
     const int m1 = (smask & 1) | (((smask >> 7) & 31) << 1);    // round 1: tile bits 0, 7..11
     const int m2 = (smask >> 1) & 63;                            // round 2: tile bits 1..6
+    const int tiles_per_row_log2 = p.d - TILE_LOG2;              // CONTIG only
+    auto contig_off = [&](int64_t t, int64_t ld) -> int64_t {
+        const int64_t row = t >> tiles_per_row_log2;
+        return row * ld + ((t - (row << tiles_per_row_log2)) << TILE_LOG2) + 2 * tg;
+    };
     T v[64];
+    const int64_t G = gridDim.x;
+    for (int64_t t = (int64_t)blockIdx.x - G; t < ntiles; t += G) {
+        const int64_t tn = t + G;
+        if (t >= 0) {
+            butterflies64_masked(v, m1);
+            asm volatile("" : "+r"(tg));
 #pragma unroll
-    for (int h = 0; h < 32; ++h) {
-        const int e = 128 * h + 2 * tg;
-        const int64_t g = fwht_map(p, t, e, ldi);
-        if (g < 0) {
-            v[2 * h] = T(0); v[2 * h + 1] = T(0);
-        } else if (vec) {
-            Elem<T>::load2(in + g, v[2 * h], v[2 * h + 1]);
-        } else {
-            v[2 * h] = Elem<T>::load1(in + g);
-            v[2 * h + 1] = Elem<T>::load1(in + g + 1);   // bit 0 is always contiguous
+            for (int r = 0; r < 64; ++r) buf[r * 64 + (tg ^ (r & M))] = v[r];
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 64; ++r) v[r] = buf[tg * 64 + (r ^ (tg & M))];
+            butterflies64_masked(v, m2);
+#pragma unroll
+            for (int r = 0; r < 64; ++r) buf[tg * 64 + (r ^ (tg & M))] = v[r] * post_scale;
+            __syncthreads();
         }
-    }
-    butterflies64_masked(v, m1);
-    asm volatile("" : "+r"(tg));
+        const bool have_next = tn < ntiles;
+        const int64_t ob = (CONTIG && t >= 0) ? contig_off(t, ldo) : 0;
+        const int64_t ib = (CONTIG && have_next) ? contig_off(tn, ldi) : 0;
 #pragma unroll
-    for (int r = 0; r < 64; ++r) buf[r * 64 + (tg ^ (r & M))] = v[r];
-    group_barrier(grp);
-#pragma unroll
-    for (int r = 0; r < 64; ++r) v[r] = buf[tg * 64 + (r ^ (tg & M))];
-    butterflies64_masked(v, m2);
-#pragma unroll
-    for (int r = 0; r < 64; ++r) buf[tg * 64 + (r ^ (tg & M))] = v[r] * post_scale;
-    group_barrier(grp);
-    // back to the round-1 layout for coalesced 16-byte stores
-#pragma unroll
-    for (int h = 0; h < 32; ++h) {
-        const int e = 128 * h + 2 * tg;
-        const int64_t g = fwht_map(p, t, e, ldo);
-        if (g < 0) continue;
-        const T a = buf[(2 * h) * 64 + (tg ^ ((2 * h) & M))];
-        const T b = buf[(2 * h + 1) * 64 + (tg ^ ((2 * h + 1) & M))];
-        if (vec) {
-            if (sizeof(T) == 8) *reinterpret_cast<double2 *>(out + g) = make_double2((double)a, (double)b);
-            else *reinterpret_cast<float2 *>(out + g) = make_float2((float)a, (float)b);
-        } else {
-            out[g] = a; out[g + 1] = b;
+        for (int h = 0; h < 32; ++h) {
+            const int e = 128 * h + 2 * tg;
+            if (t >= 0) {
+                // back to the round-1 layout for coalesced 16-byte stores
+                const int64_t g = CONTIG ? ob + 128 * h : fwht_map(p, t, e, ldo);
+                if (g >= 0) {
+                    const T a = buf[(2 * h) * 64 + (tg ^ ((2 * h) & M))];
+                    const T b = buf[(2 * h + 1) * 64 + (tg ^ ((2 * h + 1) & M))];
+                    if (CONTIG || vec) {
+                        if (sizeof(T) == 8) *reinterpret_cast<double2 *>(out + g) = make_double2((double)a, (double)b);
+                        else *reinterpret_cast<float2 *>(out + g) = make_float2((float)a, (float)b);
+                    } else {
+                        out[g] = a; out[g + 1] = b;
+                    }
+                }
+            }
+            // every path defines v[2h], v[2h+1] (nothing of the old tile stays live)
+            const int64_t g = !have_next ? -1 : (CONTIG ? ib + 128 * h : fwht_map(p, tn, e, ldi));
+            if (g < 0) {
+                v[2 * h] = T(0); v[2 * h + 1] = T(0);
+            } else if (CONTIG || vec) {
+                Elem<T>::load2(in + g, v[2 * h], v[2 * h + 1]);
+            } else {
+                v[2 * h] = Elem<T>::load1(in + g);
+                v[2 * h + 1] = Elem<T>::load1(in + g + 1);   // bit 0 is always contiguous
+            }
         }
+        __syncthreads();        // the store phase has finished reading buf before it is overwritten
     }
 }
 
@@ -144,9 +163,9 @@ static int fwht_run(const T *a, int64_t m, int64_t n, int64_t lda, T *out, int64
         RLA_CUDA_CHECK(cudaGetLastError());
         return RLA_OK;
     }
-    auto kern = fwht_pass_kernel<T>;
-    const int smem = 2 * TILE * sizeof(T);
-    RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = TILE * sizeof(T);
+    RLA_CUDA_CHECK(cudaFuncSetAttribute(fwht_pass_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    RLA_CUDA_CHECK(cudaFuncSetAttribute(fwht_pass_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int done = 0;
     bool first = true;
     while (done < d) {
@@ -163,9 +182,12 @@ static int fwht_run(const T *a, int64_t m, int64_t n, int64_t lda, T *out, int64
         const bool last = done + p.nb >= d;
         const int vec = (reinterpret_cast<uintptr_t>(src) % (2 * sizeof(T)) == 0) && (lds % 2 == 0) &&
                         (reinterpret_cast<uintptr_t>(out) % (2 * sizeof(T)) == 0) && (ldo % 2 == 0) && (n >= 2);
-        const int64_t grid = (ntiles + 1) / 2;
-        RLA_REQUIRE(grid < (int64_t(1) << 31), "rla_fwht: grid too large");
-        kern<<<(unsigned)grid, CTA, smem, st>>>(src, lds, out, ldo, p, ntiles, last ? post_scale : T(1), vec);
+        const int64_t grid = std::min<int64_t>(ntiles, (int64_t)sm_count() * 4);
+        const bool contig = first && p.nb == TILE_LOG2 && vec;
+        if (contig)
+            fwht_pass_kernel<T, true><<<(unsigned)grid, GROUP, smem, st>>>(src, lds, out, ldo, p, ntiles, last ? post_scale : T(1), vec);
+        else
+            fwht_pass_kernel<T, false><<<(unsigned)grid, GROUP, smem, st>>>(src, lds, out, ldo, p, ntiles, last ? post_scale : T(1), vec);
         count_launch();
         RLA_CUDA_CHECK(cudaGetLastError());
         done += p.nb;
