@@ -245,13 +245,14 @@ def run_ours(args):
         if rank == 0:
             sampler.start()
         l0 = lib.rla_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
             step()
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = evs[0].elapsed_time(evs[-1])                    # the K timed steps, start to end
+        timed.last_step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
         launches = lib.rla_launch_count() - l0
         clocks = sampler.stop() if rank == 0 else None
         barrier()
@@ -312,7 +313,10 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             traffic = (json.load(open(tpath)).get(name) or {}).get("bytes")
+        best = min(timed.last_step_ms) / 1e3
         roof.update(achieved=achieved, frac=achieved / roof["peak"], traffic=traffic,
+                    achieved_best_step=work / best / (1e12 if roof["bound"] == "tensor" else 1e9),
+                    step_ms=[round(v, 3) for v in timed.last_step_ms],
                     kernel="sketch_gemm_kernel" if wl["kind"] == "gauss" else "srht_main_kernel",
                     note="duration = whole step (main kernel + its small reduce/finalize kernel), CUDA events")
         res = {
