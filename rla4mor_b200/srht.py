@@ -230,3 +230,13 @@ def fht_oop(a, nthreads=1):
 def fht_ip(a):
     """In-place normalised FWHT along the last axis (rla/srht.py:99-118)."""
     return _fht(a, inplace=True)
+
+
+# The reference also defines four numba loop-order variants of the in-place transform
+# (rla/srht.py:14-96).  `_fht_2d` and `_fht_2d_sequential` are unreachable from its public
+# functions (SURVEY.md section 8a, row a5); all four compute the same normalised in-place
+# FWHT along the last axis, so they are aliases of `fht_ip` here.
+_fht_1d = fht_ip
+_fht_2d = fht_ip
+_fht_2d_sequential = fht_ip
+_fht_2d_parallel = fht_ip

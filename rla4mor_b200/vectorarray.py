@@ -105,6 +105,9 @@ class DeviceVectorArray:
         torch = _torch()
         c = torch.as_tensor(np.atleast_2d(np.asarray(coefficients)), dtype=self.data.dtype, device=self.data.device)
         assert c.shape[1] == len(self)
+        if self.data.dtype == torch.float64 and len(self) > 0:
+            from .reductor_ops import gemm_nn                  # (r', r) @ (r, n) on the sketch GEMM
+            return DeviceVectorArray(self.space, gemm_nn(c.contiguous(), self.data))
         return DeviceVectorArray(self.space, c @ self.data)
 
     def norm(self):
