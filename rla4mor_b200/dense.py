@@ -13,16 +13,10 @@ from ._lib import check, lib, stream_ptr
 KIND_NORMAL = 0
 KIND_RADEMACHER = 1
 
-_WS = {}
-
-
 def _workspace(nbytes, device):
-    key = (device.type, device.index)
-    ws = _WS.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _WS[key] = ws
-    return ws
+    """Scratch for one call, taken from torch's caching allocator: it is tied to the current
+    stream, so concurrent calls on different streams never share a buffer."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 def _rows(x):

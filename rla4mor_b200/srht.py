@@ -18,7 +18,6 @@ from collections import OrderedDict
 
 import numpy as np
 
-from . import _lib
 from ._lib import c_void_p, check, lib, require_cuda, stream_ptr
 
 
@@ -59,7 +58,6 @@ class SrhtPlan:
             check(lib().rla_srht_plan_upload(handle, self.image.data_ptr(), stream_ptr()), "rla_srht_plan_upload")
         self._signs_dev = None
         self._idx_dev = None
-        self._ws = None
 
     @property
     def signs_dev(self):
@@ -80,11 +78,10 @@ class SrhtPlan:
         return lib().rla_srht_plan_passes(self._handle)
 
     def workspace(self, m):
+        """Scratch for one call from torch's caching allocator (stream-safe, see dense._workspace)."""
         import torch
         need = lib().rla_srht_workspace_bytes(self._handle, m)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(max(need, 16), dtype=torch.uint8, device=self.device)
-        return self._ws
+        return torch.empty(max(need, 16), dtype=torch.uint8, device=self.device)
 
     def apply(self, x, scale=None, out=None):
         """x: CUDA tensor (m, n) with unit inner stride -> (m, k) sketch."""
