@@ -193,28 +193,37 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
 #pragma unroll
                     for (int r = 0; r < 64; ++r) const_cast<T *>(so[r & M])[r * 64] = v[r];
                     bar_sync(1 + q, 64);
-                    const T *rb = buf + tgo * 64;
-                    int sx[M + 1];
+                    // round 2 reads this thread's row with 16-byte loads in position order: chunk
+                    // j ^ (tg & 7) goes to register chunk j (conflict free); see tile_pos_ws()
+                    // for why the butterflies still produce the right outputs (up to signs that
+                    // the sample descriptors carry)
+                    constexpr int E = 16 / (int)sizeof(T);           // elements per 16-byte chunk
+                    using Chunk = typename Elem<T>::Chunk;
+                    Chunk *rowc = reinterpret_cast<Chunk *>(buf + tgo * 64);
+                    int cx[8];
 #pragma unroll
-                    for (int c = 0; c <= M; ++c) sx[c] = c ^ (tgo & M);
+                    for (int i = 0; i < 8; ++i) cx[i] = i ^ (tgo & 7);
 #pragma unroll
-                    for (int r = 0; r < 64; ++r) v[r] = rb[(r & ~M) + sx[r & M]];
+                    for (int j = 0; j < 64 / E; ++j) Elem<T>::unpack(rowc[(j & ~7) + cx[j & 7]], &v[E * j]);
                     butterflies64(v);                           // tile bits 1..6
-                    // write-back; when the next tile of this group is a fast one, its loads are
-                    // issued pair by pair right behind the stores that free the registers
+                    // write-back to the same chunks; when the next tile of this group is a fast
+                    // one, its loads are issued right behind the stores that free the registers
                     const int64_t jn2 = tile_of(t + WS_GROUPS);
                     if (t + WS_GROUPS < ntl && jn2 < a.ntiles_valid && is_fast(jn2)) {
                         const T *np_ = rowp + jn2 * TILE + 2 * tg;
 #pragma unroll
-                        for (int h = 0; h < 32; ++h) {
-                            const_cast<T *>(rb)[((2 * h) & ~M) + sx[(2 * h) & M]] = v[2 * h];
-                            const_cast<T *>(rb)[((2 * h + 1) & ~M) + sx[(2 * h + 1) & M]] = v[2 * h + 1];
-                            Elem<T>::load2(np_ + 128 * h, v[2 * h], v[2 * h + 1]);
+                        for (int j = 0; j < 64 / E; ++j) {
+                            rowc[(j & ~7) + cx[j & 7]] = Elem<T>::pack(&v[E * j]);
+#pragma unroll
+                            for (int i = 0; i < E / 2; ++i) {
+                                const int h = (E * j) / 2 + i;
+                                Elem<T>::load2(np_ + 128 * h, v[2 * h], v[2 * h + 1]);
+                            }
                         }
                         loaded = true;
                     } else {
 #pragma unroll
-                        for (int r = 0; r < 64; ++r) const_cast<T *>(rb)[(r & ~M) + sx[r & M]] = v[r];
+                        for (int j = 0; j < 64 / E; ++j) rowc[(j & ~7) + cx[j & 7]] = Elem<T>::pack(&v[E * j]);
                     }
                 }
                 // A_q: the transformed tile is in shared memory
@@ -271,7 +280,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) srht_ws_kernel(const SrhtArgs<T
     T *wsp = a.ws + ((chunk * a.m + row) * (int64_t)(NSLOT * CTA));
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
-        const uint32_t par = __popc((dsc[s] >> TILE_LOG2) & jlast) & 1u;
+        // bit 31 of the descriptor: sign twist of the round-2 output (tile_pos_ws)
+        const uint32_t par = (__popc((dsc[s] >> TILE_LOG2) & jlast) ^ (dsc[s] >> 31)) & 1u;
         wsp[s * CTA + gt] = xor_sign(acc[s], par << 31);
     }
 }
@@ -323,14 +333,22 @@ struct rla_srht_plan {
 static size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
 // slot assignment: lane (tid % lanes) should equal the bank group of the gathered word
-static void build_desc_set(rla_srht_plan *p, const SrhtDescSet &set, const std::vector<int64_t> &uniq,
-                           const int64_t *idx, int64_t per_pass) {
+static void build_desc_set(rla_srht_plan *p, const SrhtDescSet &set, bool ws_layout,
+                           const std::vector<int64_t> &uniq, const int64_t *idx, int64_t per_pass) {
     const int mask = p->elem_bytes == 8 ? 15 : 31;
     const int lanes = mask + 1;                // lanes per shared-memory wavefront
     const int nst = set.nslot * CTA;
     uint32_t *desc = reinterpret_cast<uint32_t *>(p->image.data() + set.off_desc);
     std::vector<int32_t> slot_of_uniq(uniq.size());
     const int threads_per_bucket = CTA / lanes;
+    // descriptor of one distinct sample: bits 0..11 position in the tile buffer, bits 12..30 the
+    // tile-index bits sh, bit 31 (warp-specialised layout only) a sign folded in at the end
+    auto make_desc = [&](int64_t s) -> uint32_t {
+        const int e = (int)(s & (TILE - 1));
+        int neg = 0;
+        const int pos = ws_layout ? tile_pos_ws(e, p->elem_bytes, &neg) : tile_pos(e, mask);
+        return (uint32_t)pos | ((uint32_t)(s >> TILE_LOG2) << TILE_LOG2) | ((uint32_t)neg << 31);
+    };
     for (int pass = 0; pass < p->npass; ++pass) {
         const int64_t u0 = pass * per_pass, u1 = std::min<int64_t>(p->nuniq, u0 + per_pass);
         std::vector<int> cnt(lanes, 0);
@@ -338,14 +356,14 @@ static void build_desc_set(rla_srht_plan *p, const SrhtDescSet &set, const std::
         std::vector<int64_t> overflow;
         const int cap = set.nslot * threads_per_bucket;
         for (int64_t u = u0; u < u1; ++u) {
-            const int pos = tile_pos((int)(uniq[u] & (TILE - 1)), mask);
-            const int b = pos & mask;
+            const uint32_t dsc = make_desc(uniq[u]);
+            const int b = (int)(dsc & (uint32_t)mask);
             if (cnt[b] < cap) {
                 const int c = cnt[b]++;
                 const int tid = b + lanes * (c % threads_per_bucket), s = c / threads_per_bucket;
                 const int cell = s * CTA + tid;
                 used[cell] = 1;
-                desc[(size_t)pass * nst + cell] = (uint32_t)pos | ((uint32_t)(uniq[u] >> TILE_LOG2) << TILE_LOG2);
+                desc[(size_t)pass * nst + cell] = dsc;
                 slot_of_uniq[u] = pass * nst + cell;
             } else {
                 overflow.push_back(u);
@@ -355,8 +373,7 @@ static void build_desc_set(rla_srht_plan *p, const SrhtDescSet &set, const std::
         for (int64_t u : overflow) {           // bucket full: any free cell (costs a bank conflict)
             while (used[cell]) ++cell;
             used[cell] = 1;
-            const int pos = tile_pos((int)(uniq[u] & (TILE - 1)), mask);
-            desc[(size_t)pass * nst + cell] = (uint32_t)pos | ((uint32_t)(uniq[u] >> TILE_LOG2) << TILE_LOG2);
+            desc[(size_t)pass * nst + cell] = make_desc(uniq[u]);
             slot_of_uniq[u] = pass * nst + cell;
         }
     }
@@ -414,7 +431,8 @@ extern "C" int rla_srht_plan_create(rla_srht_plan **out, const int8_t *signs, in
             sw[jh * GROUP + tg] |= uint64_t(1) << (2 * h + l);
         }
     }
-    for (const SrhtDescSet &set : p->sets) build_desc_set(p, set, uniq, idx, per_pass);
+    build_desc_set(p, p->sets[0], false, uniq, idx, per_pass);
+    build_desc_set(p, p->sets[1], true, uniq, idx, per_pass);
     *out = p;
     return RLA_OK;
 }

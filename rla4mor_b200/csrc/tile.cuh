@@ -22,9 +22,32 @@ __host__ __device__ __forceinline__ int tile_pos(int e, int mask) {
     return B * 64 + (A ^ (B & mask));
 }
 
+// Final position (and sign twist) of tile element e in the warp-specialised SRHT kernel.
+// Round 2 of that kernel reads its row of the exchange buffer with 16-byte loads in POSITION
+// order instead of logical order; the row holds logical index A at position A ^ (B & mask),
+// and the thread reads 16-byte chunk j ^ (B & 7) into register chunk j (bank-conflict free),
+// so register p holds logical A = p ^ c with c = (B & mask) ^ ((B & 7) << log2 E)
+// (E = elements per 16 bytes).  Butterflies are invariant under XOR relabelling up to signs:
+// H P_c = D_c H with D_c = diag((-1)^popcount(s & c)), so the registers end up holding
+// z[s] = (-1)^popcount(s & c) y[s] at the natural output index s.  z is written back chunk by
+// chunk to the positions it was read from; the sign is folded into the sample descriptor.
+__host__ __device__ __forceinline__ int tile_pos_ws(int e, int elem_bytes, int *negate) {
+    const int mask = elem_bytes == 8 ? 15 : 31, le = elem_bytes == 8 ? 1 : 2, E = 1 << le;
+    const int A = (e >> 1) & 63;                       // logical output index s of round 2
+    const int B = (e & 1) | ((e >> 7) << 1);           // round-2 thread (row of the buffer)
+    const int c = (B & mask) ^ ((B & 7) << le);
+    int v = A & c, par = 0;
+    while (v) { par ^= v & 1; v >>= 1; }
+    *negate = par;
+    return B * 64 + ((((A >> le) ^ (B & 7)) << le) | (A & (E - 1)));
+}
+
 template <typename T> struct Elem;
 template <> struct Elem<double> {
     static constexpr int MASK = 15;
+    using Chunk = double2;                             // 16 bytes of shared memory
+    __device__ static __forceinline__ void unpack(const double2 &c, double *v) { v[0] = c.x; v[1] = c.y; }
+    __device__ static __forceinline__ double2 pack(const double *v) { return make_double2(v[0], v[1]); }
     __device__ static __forceinline__ void load2(const double *p, double &a, double &b) {
         double2 v = ldg_stream_f64x2(p); a = v.x; b = v.y;
     }
@@ -32,6 +55,9 @@ template <> struct Elem<double> {
 };
 template <> struct Elem<float> {
     static constexpr int MASK = 31;
+    using Chunk = float4;
+    __device__ static __forceinline__ void unpack(const float4 &c, float *v) { v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w; }
+    __device__ static __forceinline__ float4 pack(const float *v) { return make_float4(v[0], v[1], v[2], v[3]); }
     __device__ static __forceinline__ void load2(const float *p, float &a, float &b) {
         float2 v;
         asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
