@@ -61,9 +61,15 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise RlaError(
-                f"{LIB_PATH} is missing: build it with `python -m rla4mor_b200._build` "
-                "(there is no CPU fallback for the sketching kernels)")
+            # a fresh checkout has no binary: compile the CUDA sources once (needs nvcc);
+            # there is no CPU fallback, so without the library every call fails
+            try:
+                from . import _build
+                _build.build_library()
+            except Exception as exc:
+                raise RlaError(
+                    f"{LIB_PATH} is missing and could not be built ({exc}); build it with "
+                    "`python -m rla4mor_b200._build` (there is no CPU fallback for the sketching kernels)") from exc
         handle = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGS.items():
             fn = getattr(handle, name)
