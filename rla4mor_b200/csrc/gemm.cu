@@ -13,12 +13,17 @@
 //   * U (and Theta when explicit) stream through a 4-stage shared-memory ring of
 //     [rows x 16 doubles] boxes written by TMA (cp.async.bulk.tensor, 128-byte swizzle,
 //     out-of-range rows/columns zero-filled by the TMA unit: ragged m, k, n for free).
-//   * warp tile 64 x 32: per 16-wide k block a thread reads, for each of its 8 row groups,
-//     the 4 consecutive doubles k = 4t..4t+3 (two conflict-free LDS.128) and issues
-//     mma.sync.m8n8k4.f64 for the 4 k sub-steps (the k permutation inside a block is
-//     free as long as A and B fragments agree).  Accumulators: 64 doubles per thread.
-//   * on-the-fly Theta: the B fragment of a thread is Theta[row = nbase+8i+g, 4t..4t+3]
-//     = exactly one Philox block -> 4 normals, produced in registers, never in memory.
+//   * 8 consumer warps, warp tile 64 x 32 (64 accumulator doubles per thread), issue
+//     mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Fragments are held per 8-wide half of the 16-wide
+//     k block, double buffered: in half h a thread owns k = 4t + 2h + {0,1} of every row, i.e.
+//     one conflict-free ld.shared.v2.f64 per row and half (the k permutation inside a block is
+//     free as long as A and B fragments agree).  Full warp tiles run with no predicate or
+//     branch between the DMMAs.
+//   * 4 producer warps: lane 0 of the first issues the TMA loads; with on-the-fly Theta all
+//     128 producer threads generate the [BN x 16] Theta tile of the stage (one sketch row each,
+//     four Philox blocks -> Box-Muller) straight into the swizzled layout the consumers read.
+//     Theta is never in memory; rla_theta_materialize_f64 exports the same values for parity.
+//   * setmaxnreg: consumers 232 registers, producers 40.
 #include "common.cuh"
 #include "rng.cuh"
 #include <cuda.h>
@@ -72,16 +77,6 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 __device__ __forceinline__ void lds_f64x2(uint32_t addr, double2 &v) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
 }
-// 4 consecutive doubles k = 4t..4t+3 of row `row` of a [rows][16] box stored with the
-// 128-byte TMA swizzle (16-byte chunk index XOR (row & 7))
-__device__ __forceinline__ void lds_row4(const double *tile, int row, int t, double (&v)[4]) {
-    const char *base = reinterpret_cast<const char *>(tile) + row * 128;
-    const int sw = row & 7;
-    const double2 lo = *reinterpret_cast<const double2 *>(base + (((2 * t) ^ sw) << 4));
-    const double2 hi = *reinterpret_cast<const double2 *>(base + (((2 * t + 1) ^ sw) << 4));
-    v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
-}
-
 struct GemmArgs {
     int64_t m, k, n;          // Y is m x k, reduction over n
     int64_t kper;             // 16-wide k blocks per chunk
