@@ -199,6 +199,30 @@ int rla_residual_norm_f64(const double *S_dev, int64_t Q, int64_t k, int64_t r,
                           const double *b_dev, int64_t P, const double *tr_dev,
                           double *out_dev, void *stream);
 
+/* ------------------------------------------- row-sharded exchange (K5) -----
+ * The one exchange step of the row-sharded sketch (no reference
+ * analogue: the reference is single-process).  Each rank owns ONE peer buffer (cudaMalloc,
+ * zero-filled) that the other ranks of the node map through CUDA IPC:
+ *   rla_peer_buffer_create  allocates it and returns the 64-byte IPC handle to hand to the peers,
+ *   rla_peer_buffer_open    maps a peer's buffer into this process (NVLink P2P),
+ *   rla_peer_buffer_close / _destroy  undo the two.
+ * rla_peer_allreduce_f64 sums the (m, k) partial sketches of all ranks in rank order into
+ * out_dev (bit-identical on every rank): part_ptrs[p] / flag_ptrs[p] are HOST arrays of this
+ * process's device addresses of rank p's partial and of rank p's flag row (>= world uint64,
+ * zero before the first call); `epoch` must be 1, 2, 3, ... over successive calls on the same
+ * flag rows and the caller alternates between two partial buffers by epoch parity.
+ * high_dev (k int32, may be NULL): sample i of rank p's partial is multiplied by
+ * (-1)^popcount(high_dev[i] & p), the slab factor of H_{2^d} = H_G (x) H_{2^d/G}.
+ * status_dev: one int32 set to 1 if a peer did not publish within timeout_s seconds. */
+int rla_peer_buffer_create(size_t bytes, void **dev_ptr, unsigned char *handle64);
+int rla_peer_buffer_open(const unsigned char *handle64, void **dev_ptr);
+int rla_peer_buffer_close(void *dev_ptr);
+int rla_peer_buffer_destroy(void *dev_ptr);
+int rla_peer_allreduce_f64(const void *const *part_ptrs, void *const *flag_ptrs, int world, int rank,
+                           uint64_t epoch, int64_t m, int64_t k, int64_t ldp,
+                           const int32_t *high_dev, double *out_dev, int64_t ldo,
+                           int *status_dev, double timeout_s, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,12 @@ _SIGS = {
     "rla_svd_jacobi_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, _vp, c_int, c_double,
                                    POINTER(c_int), _vp]),
     "rla_residual_norm_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int64, _vp, _vp, _vp]),
+    "rla_peer_buffer_create": (c_int, [c_size_t, POINTER(c_void_p), _vp]),
+    "rla_peer_buffer_open": (c_int, [_vp, POINTER(c_void_p)]),
+    "rla_peer_buffer_close": (c_int, [_vp]),
+    "rla_peer_buffer_destroy": (c_int, [_vp]),
+    "rla_peer_allreduce_f64": (c_int, [_vp, _vp, c_int, c_int, c_uint64, c_int64, c_int64, c_int64, _vp, _vp, c_int64,
+                                       _vp, c_double, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

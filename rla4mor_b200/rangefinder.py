@@ -18,8 +18,10 @@ from . import reductor_ops as ops
 from . import sharding
 
 
-def sketch_block(U_local, n, k, seed, kind="srht", rank=0, world=1, group=None):
-    """(m, k) sketch of the block whose slab `U_local` (m, hi - lo) lives on this rank."""
+def sketch_block(U_local, n, k, seed, kind="srht", rank=0, world=1, group=None, reducer=None):
+    """(m, k) sketch of the block whose slab `U_local` (m, hi - lo) lives on this rank.
+    `reducer` (peer.PeerSketchReducer): exchange the partials over NVLink peer memory
+    (csrc/peer.cu) instead of an NCCL all-reduce."""
     if world == 1:
         if kind == "srht":
             from .srht import get_plan
@@ -27,16 +29,29 @@ def sketch_block(U_local, n, k, seed, kind="srht", rank=0, world=1, group=None):
         from . import dense
         return dense.embed_apply_rng(seed, 1 if kind == "rademacher" else 0, 1.0 / np.sqrt(k), k, U_local)
     if kind == "srht":
-        return sharding.srht_row_sharded(U_local, n, k, seed, rank, world, group)
-    return sharding.gaussian_row_sharded(U_local, n, k, seed, rank, world, 1 if kind == "rademacher" else 0, group)
+        return sharding.srht_row_sharded(U_local, n, k, seed, rank, world, group, reducer)
+    return sharding.gaussian_row_sharded(U_local, n, k, seed, rank, world, 1 if kind == "rademacher" else 0, group,
+                                         reducer)
 
 
-def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, group=None, svd=True):
+def thin_qr(S):
+    """Thin QR of the k x m sketch held as the row block S (m, k): S = R^T Q, Q (m, k) with
+    orthonormal rows, R (m, m) upper triangular (pyMOR gram_schmidt's convention,
+    mor/sketched_reductor.py:94)."""
+    return ops.gram_schmidt(S)
+
+
+def sketch_svd(S, want_v=True):
+    """SVD of the sketch (see reductor_ops.svd_jacobi)."""
+    return ops.svd_jacobi(S, want_v=want_v)
+
+
+def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, group=None, svd=True, reducer=None):
     """Returns dict(sketch, Q, R, T[, s, W]) -- all small (m x k, m x m) device tensors."""
-    S = sketch_block(U_local, n, k, seed, kind, rank, world, group)
-    Q, R = ops.gram_schmidt(S)
+    S = sketch_block(U_local, n, k, seed, kind, rank, world, group, reducer)
+    Q, R = thin_qr(S)
     out = {"sketch": S, "Q": Q, "R": R, "T": torch.linalg.pinv(R)}
     if svd:
-        Urows, s, W = ops.svd_jacobi(S, want_v=True)
+        Urows, s, W = sketch_svd(S, want_v=True)
         out.update(s=s, W=W, Urows=Urows)
     return out

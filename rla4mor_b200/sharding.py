@@ -81,35 +81,75 @@ def row_sharded_sketch(local_sketch, factor=None, group=None):
 
 
 # --------------------------------------------------------------------- device front ends
-def srht_row_sharded(x_slab, n, k, seed, rank, world, group=None):
-    """Row-sharded SRHT on the GPU: x_slab is this rank's (m, hi - lo) CUDA slab."""
+def srht_row_sharded(x_slab, n, k, seed, rank, world, group=None, reducer=None):
+    """Row-sharded SRHT on the GPU: x_slab is this rank's (m, hi - lo) CUDA slab.
+
+    With `reducer` (a peer.PeerSketchReducer for this (m, k)) the local kernel writes its
+    partial into peer-mapped memory and ONE kernel applies the slab signs and sums over
+    NVLink (csrc/peer.cu); without it the partial is scaled and all-reduced by NCCL."""
     import torch
     from .srht import SrhtPlan, draw_signs_and_indices
-    signs, sampling = draw_signs_and_indices(n, k, seed)
-    lo, hi, lsigns, lidx, fac = srht_slab_descriptor(signs, sampling, n, rank, world)
     m = x_slab.shape[0]
+    slab, ranges = srht_slabs(n, world)
+    lo, hi = ranges[rank]
+    key = (int(n), int(k), None if seed is None else int(seed), int(rank), int(world), x_slab.dtype, x_slab.device.index)
+    desc = _SLAB_PLANS.get(key) if seed is not None else None
+    if desc is None:
+        # the host draws cost seconds at n = 2**24: once per (seed, n, k, rank, world)
+        signs, sampling = draw_signs_and_indices(n, k, seed)
+        _, _, lsigns, lidx, fac = srht_slab_descriptor(signs, sampling, n, rank, world)
+        plan = None
+        if hi > lo:
+            if hi - lo < slab:
+                lsigns = np.concatenate([lsigns, np.ones(slab - (hi - lo), dtype=lsigns.dtype)])
+            plan = SrhtPlan(slab, k, lsigns, lidx, x_slab.dtype, x_slab.device)
+        factor = torch.as_tensor(fac, dtype=x_slab.dtype, device=x_slab.device)
+        high = torch.as_tensor((np.asarray(sampling, dtype=np.int64) // slab).astype(np.int32), device=x_slab.device)
+        desc = (plan, factor, high)
+        if seed is not None:
+            _SLAB_PLANS[key] = desc
+            while len(_SLAB_PLANS) > 8:
+                _SLAB_PLANS.pop(next(iter(_SLAB_PLANS)))
+    plan, factor, high = desc
+    if hi > lo:
+        assert x_slab.shape[1] == hi - lo
+        if hi - lo < slab:
+            # ragged last slab: pad to the slab length so the local indices stay in range
+            xp = torch.zeros((m, slab), dtype=x_slab.dtype, device=x_slab.device)
+            xp[:, :hi - lo] = x_slab
+            x_slab = xp
+    scale = 1.0 / np.sqrt(k)
+    if reducer is not None:
+        assert x_slab.dtype == torch.float64 and (reducer.m, reducer.k) == (m, k)
+        part = reducer.partial()
+        if hi > lo:
+            plan.apply(x_slab, scale=scale, out=part)
+        else:
+            part.zero_()
+        return reducer.reduce(high=high)
     if hi <= lo:
-        part = torch.zeros((m, k), dtype=x_slab.dtype, device=x_slab.device)
-        return all_reduce_sum(part, group)
-    assert x_slab.shape[1] == hi - lo
-    slab = srht_slabs(n, world)[0]
-    if hi - lo < slab:
-        # ragged last slab: pad to the slab length so the local indices stay in range
-        xp = torch.zeros((m, slab), dtype=x_slab.dtype, device=x_slab.device)
-        xp[:, :hi - lo] = x_slab
-        x_slab = xp
-        lsigns = np.concatenate([lsigns, np.ones(slab - (hi - lo), dtype=lsigns.dtype)])
-    plan = SrhtPlan(x_slab.shape[1], k, lsigns, lidx, x_slab.dtype, x_slab.device)
-    fac_t = torch.as_tensor(fac, dtype=x_slab.dtype, device=x_slab.device)
-    return row_sharded_sketch(lambda: plan.apply(x_slab, scale=1.0 / np.sqrt(k)), fac_t, group)
+        return all_reduce_sum(torch.zeros((m, k), dtype=x_slab.dtype, device=x_slab.device), group)
+    return row_sharded_sketch(lambda: plan.apply(x_slab, scale=scale), factor, group)
 
 
-def gaussian_row_sharded(x_slab, n, k, seed, rank, world, kind=0, group=None):
-    """Row-sharded on-the-fly Gaussian / Rademacher sketch on the GPU."""
+_SLAB_PLANS = {}
+
+
+def gaussian_row_sharded(x_slab, n, k, seed, rank, world, kind=0, group=None, reducer=None):
+    """Row-sharded on-the-fly Gaussian / Rademacher sketch on the GPU (`reducer`: see srht_row_sharded)."""
     import torch
     from . import dense
     lo, hi = gaussian_slabs(n, world)[rank]
     m = x_slab.shape[0]
+    if reducer is not None:
+        assert (reducer.m, reducer.k) == (m, k)
+        part = reducer.partial()
+        if hi > lo:
+            assert x_slab.shape[1] == hi - lo
+            dense.embed_apply_rng(seed, kind, 1.0 / np.sqrt(k), k, x_slab, col0=lo, out=part)
+        else:
+            part.zero_()
+        return reducer.reduce()
     if hi <= lo:
         return all_reduce_sum(torch.zeros((m, k), dtype=torch.float64, device=x_slab.device), group)
     assert x_slab.shape[1] == hi - lo

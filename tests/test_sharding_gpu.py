@@ -41,9 +41,25 @@ def _worker(rank, world, port, n, k, seed, out):
         # row-sharded on-the-fly Gaussian
         ga, gb = sharding.gaussian_slabs(n, world)[rank]
         yg = sharding.gaussian_row_sharded(torch.from_numpy(np.ascontiguousarray(x[:, ga:gb])).cuda(), n, k, seed, rank, world)
+        # the same two through the NVLink peer-memory exchange (csrc/peer.cu), three epochs
+        from rla4mor_b200.peer import PeerSketchReducer
+        red = PeerSketchReducer(6, k)
+        xs = torch.from_numpy(np.ascontiguousarray(x[:, a:b])).cuda()
+        xg = torch.from_numpy(np.ascontiguousarray(x[:, ga:gb])).cuda()
+        ps = sharding.srht_row_sharded(xs, n, k, seed, rank, world, reducer=red).clone()
+        pg = sharding.gaussian_row_sharded(xg, n, k, seed, rank, world, reducer=red).clone()
+        ps2 = sharding.srht_row_sharded(xs, n, k, seed, rank, world, reducer=red).clone()
+        red.check_status()
+        same = torch.tensor([float(torch.equal(ps, ps2))], device="cuda")
+        gathered = [torch.empty_like(ps) for _ in range(world)]
+        dist.all_gather(gathered, ps)
+        same *= float(all(torch.equal(g, ps) for g in gathered))     # bit-identical on every rank
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        red.close()
         if rank == 0:
             full = dense.embed_apply_rng(seed, 0, 1.0 / np.sqrt(k), k, torch.from_numpy(x).cuda())
-            np.savez(out, yc=yc.cpu().numpy(), ys=ys.cpu().numpy(), yg=yg.cpu().numpy(), full=full.cpu().numpy())
+            np.savez(out, yc=yc.cpu().numpy(), ys=ys.cpu().numpy(), yg=yg.cpu().numpy(), full=full.cpu().numpy(),
+                     ps=ps.cpu().numpy(), pg=pg.cpu().numpy(), same=same.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
@@ -61,6 +77,9 @@ def test_two_gpu_sharding(tmp_path, n):
     assert rel_fro(z["yc"], ref) < 1e-12
     assert rel_fro(z["ys"], ref) < 1e-12
     assert rel_fro(z["yg"], z["full"]) < 1e-12
+    assert rel_fro(z["ps"], ref) < 1e-12                             # peer-memory exchange, SRHT slab signs in-kernel
+    assert rel_fro(z["pg"], z["full"]) < 1e-12
+    assert z["same"][0] == 1.0                                       # deterministic and identical on all ranks
 
 
 def test_streaming_host_block():
