@@ -191,6 +191,28 @@ int rla_svd_jacobi_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
                        double *s_dev, double *V_dev, const int32_t *pairs_dev, int32_t *rot_dev,
                        int max_sweeps, double tol, int *sweeps_done, void *stream);
 
+/* Grid-synchronised (cooperative-launch) versions of the two factorisations (csrc/factor.cu).
+ * rla_gram_schmidt_ws_f64: same contract as rla_gram_schmidt_f64, rows dealt to many CTAs with
+ * one grid barrier per row (right-looking modified Gram-Schmidt, pyMOR's removal / re-iteration
+ * tests); falls back to the one-CTA kernel when the shape is out of range or ws is too small
+ * (rla_gram_schmidt_workspace_bytes returns 0 when the grid kernel does not apply). */
+size_t rla_gram_schmidt_workspace_bytes(int64_t r, int64_t k);
+int rla_gram_schmidt_ws_f64(double *a_dev, int64_t r, int64_t k, int64_t lda, int64_t offset,
+                            double *R_dev, int32_t *flags_dev,
+                            double atol, double rtol, double reiteration_threshold,
+                            void *ws_dev, size_t ws_bytes, void *stream);
+/* Block one-sided Jacobi SVD in ONE launch (same data convention as rla_svd_jacobi_f64):
+ * B = rla_svd_jacobi_block_rows(k, m, want_v) rows per block (0: shape not supported, use
+ * rla_svd_jacobi_f64); sched_dev: round-robin schedule over nb = ceil(m / B) rounded up to even
+ * blocks, (nb - 1) rounds x (nb / 2) int32 pairs, (b, -1) marking the bye of block b;
+ * scratch_dev: rla_svd_jacobi_block_scratch_ints(m, B, max_sweeps) int32; on return
+ * scratch_dev[0..2] = {sweeps done, converged, timeout}.  No host synchronisation. */
+int rla_svd_jacobi_block_rows(int64_t k, int64_t m, int want_v);
+size_t rla_svd_jacobi_block_scratch_ints(int64_t m, int B, int max_sweeps);
+int rla_svd_jacobi_block_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
+                             double *s_dev, double *V_dev, const int32_t *sched_dev, int B,
+                             int32_t *scratch_dev, int max_sweeps, double tol, void *stream);
+
 /* Sketched residual norm  || sum_q th[q] S_q a - sum_p tr[p] b_p ||_2
  * (ResidualErrorEstimator.estimate_error, mor/sketched_reductor.py:216-219);
  * S_dev is Q contiguous k x r row-major blocks, b_dev P contiguous k-vectors. */

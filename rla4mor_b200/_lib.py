@@ -51,6 +51,12 @@ _SIGS = {
     "rla_svd_jacobi_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, _vp, c_int, c_double,
                                    POINTER(c_int), _vp]),
     "rla_residual_norm_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int64, _vp, _vp, _vp]),
+    "rla_gram_schmidt_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "rla_gram_schmidt_ws_f64": (c_int, [_vp, c_int64, c_int64, c_int64, c_int64, _vp, _vp, c_double, c_double, c_double,
+                                        _vp, c_size_t, _vp]),
+    "rla_svd_jacobi_block_rows": (c_int, [c_int64, c_int64, c_int]),
+    "rla_svd_jacobi_block_scratch_ints": (c_size_t, [c_int64, c_int, c_int]),
+    "rla_svd_jacobi_block_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, c_int, c_double, _vp]),
     "rla_peer_buffer_create": (c_int, [c_size_t, POINTER(c_void_p), _vp]),
     "rla_peer_buffer_open": (c_int, [_vp, POINTER(c_void_p)]),
     "rla_peer_buffer_close": (c_int, [_vp]),

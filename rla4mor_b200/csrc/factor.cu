@@ -1,0 +1,666 @@
+// factor.cu -- the small factorisations of the (m, k) sketch as ONE persistent, grid-synchronised
+// kernel each (cooperative launch): Gram-Schmidt with pyMOR's semantics
+// (mor/sketched_reductor.py:94) and a block one-sided Jacobi SVD (the "thin QR / SVD of the
+// k x m sketch" of BASELINE configs[4]).  Both are latency-bound: what matters is the number and
+// the cost of the sequential synchronisation points, not flops or bytes.
+//
+//  * gs_grid_kernel: RIGHT-looking modified Gram-Schmidt.  Rows are dealt round-robin to G CTAs and
+//    live in registers.  Step i: the owner of row i normalises it and publishes q_i (one grid
+//    barrier); every CTA then projects q_i out of the rows it owns (all its dot products in one
+//    block reduction).  Row i has then received exactly the projections j = 0..i-1, in that order,
+//    that pyMOR's left-looking loop applies, so R, the removal test (norm <= rtol * initial) and the
+//    re-iteration test (norm < threshold * old norm) are pyMOR's.  A re-iteration pass (rare for
+//    well-conditioned blocks) is done by the whole grid at once: every CTA computes the
+//    coefficients against the final rows it owns and a partial correction, the owner sums the
+//    partials in CTA order.  (pyMOR re-iterates with sequential MGS; the second-pass coefficients
+//    are O(eps), so the two differ by O(eps^2).)  About one barrier per row instead of i block
+//    reductions per row: 256 x 1024 in about a millisecond instead of 18 ms.
+//
+//  * jacobi_block_kernel: rows are grouped in blocks of B; a CTA holds a PAIR of blocks (2B rows of
+//    the sketch and of the accumulated rotations) in shared memory and rotates all B*B cross pairs
+//    (and, once per sweep, the pairs inside each block) with one warp per pair and CTA-local
+//    barriers only.  Block pairs follow a round-robin schedule with one grid barrier per block
+//    round: (m/B - 1) barriers per sweep instead of (m - 1) kernel launches, convergence is tested
+//    on the device (no host synchronisation), singular values come out of the same launch.
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+
+namespace cg = cooperative_groups;
+
+namespace rla {
+
+__device__ __forceinline__ double ldcg_f64(const double *p) { return __ldcg(p); }
+
+__device__ __forceinline__ int ld_acquire_gpu_i32(const int32_t *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_i32(int32_t *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(int32_t *p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Block-wide wait until *flag >= want (thread 0 polls with acquire loads; a wall-clock timeout
+// turns a protocol error into an error code instead of a hung GPU).  Returns the value seen,
+// or -1 on timeout.  All threads get the same result.
+__device__ __forceinline__ int block_wait_ge(const int32_t *flag, int want, unsigned long long timeout_ns, int *s_slot) {
+    if (threadIdx.x == 0) {
+        int v = ld_acquire_gpu_i32(flag);
+        if (v < want) {
+            const unsigned long long t0 = gtimer_ns();
+            while ((v = ld_acquire_gpu_i32(flag)) < want) {
+                if (gtimer_ns() - t0 > timeout_ns) { v = -1; break; }
+            }
+        }
+        *s_slot = v;
+    }
+    __syncthreads();
+    const int v = *s_slot;
+    __syncthreads();
+    return v;
+}
+
+// arrive-and-wait barrier over the G CTAs of a cooperative launch on a monotone counter
+__device__ __forceinline__ int grid_barrier(int32_t *ctr, int &target, int G, unsigned long long timeout_ns, int *s_slot) {
+    __threadfence();
+    __syncthreads();
+    target += G;
+    if (threadIdx.x == 0) red_release_gpu_add(ctr, 1);
+    return block_wait_ge(ctr, target, timeout_ns, s_slot);
+}
+
+// deterministic block sums of N values at once: shuffle tree in the warp, warp partials in warp order
+template <int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double (*red)[32]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) v[n] += __shfl_xor_sync(0xffffffffu, v[n], off);
+    }
+    __syncthreads();                                   // previous readers of `red` are done
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) red[n][warp] = v[n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += red[n][w];
+        v[n] = s;
+    }
+}
+
+constexpr int GS_MAX_REITER = 3;
+enum { GS_REMOVED = 1, GS_FINAL = 2, GS_REITER = 3 };
+
+// Workspace: scratch G*k doubles | coef r doubles | ctrl (GS_MAX_REITER+1)*r int32 | done (same) | status int32.
+// ctrl[e]: decision of event e (0 = not yet published); done[e]: CTAs that contributed to re-iteration e.
+template <int RPC, int EPT>
+__global__ void __launch_bounds__(256, 1)
+gs_grid_kernel(double *A, int64_t r, int64_t k, int64_t lda, int64_t offset, double *R,
+               int32_t *flags, double atol, double rtol, double thr, double *scratch, double *coef,
+               int32_t *ctrl, int32_t *done, int32_t *status, unsigned long long timeout_ns) {
+    // (no __restrict__: other CTAs write these buffers while the kernel runs)
+    __shared__ double red[RPC][32];
+    __shared__ int s_slot;
+    const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    double x[RPC][EPT];
+    double init[RPC], nrm[RPC];
+    int state[RPC];                                    // 0 pending, 1 final (orthonormal), 2 removed / absent
+
+    {
+        double ss[RPC];
+#pragma unroll
+        for (int s = 0; s < RPC; ++s) {
+            const int64_t l = (int64_t)s * G + cta;
+            ss[s] = 0.0;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int64_t c = tid + (int64_t)e * nthr;
+                x[s][e] = (l < r && c < k) ? A[l * lda + c] : 0.0;
+                ss[s] = fma(x[s][e], x[s][e], ss[s]);
+            }
+            // column l of R belongs to this CTA alone: identity, then += as projections arrive
+            if (l < r)
+                for (int64_t j = tid; j < r; j += nthr) R[j * r + l] = (j == l) ? 1.0 : 0.0;
+        }
+        block_sum_n<RPC>(ss, red);
+#pragma unroll
+        for (int s = 0; s < RPC; ++s) {
+            const int64_t l = (int64_t)s * G + cta;
+            init[s] = nrm[s] = sqrt(ss[s]);
+            state[s] = l >= r ? 2 : (l < offset ? 1 : (init[s] <= atol ? 2 : 0));
+            if (l < r && tid == 0) flags[l] = (state[s] == 2) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+
+    // owner side of one decision event for row i (slot sl of this CTA); publishes ctrl[e]
+    auto decide = [&](int64_t i, int sl, int iter, int64_t e) {
+        int d = GS_REMOVED;
+#pragma unroll
+        for (int s = 0; s < RPC; ++s) {
+            if (s != sl) continue;
+            if (state[s] == 2) continue;
+            double ss[1] = {0.0};
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) ss[0] = fma(x[s][q], x[s][q], ss[0]);
+            block_sum_n<1>(ss, red);
+            const double norm = sqrt(ss[0]), old = nrm[s];
+            nrm[s] = norm;
+            if (norm <= rtol * init[s]) d = GS_REMOVED;
+            else if (!(norm < thr * old) || iter >= GS_MAX_REITER) d = GS_FINAL;
+            else d = GS_REITER;
+            if (d == GS_FINAL) {
+                const double inv = 1.0 / norm;
+#pragma unroll
+                for (int q = 0; q < EPT; ++q) x[s][q] *= inv;
+                if (tid == 0) R[i * r + i] = norm;
+                state[s] = 1;
+            }
+            if (d == GS_REMOVED) {
+                if (tid == 0) flags[i] = 1;
+                state[s] = 2;
+            } else {
+#pragma unroll
+                for (int q = 0; q < EPT; ++q) {
+                    const int64_t c = tid + (int64_t)q * nthr;
+                    if (c < k) A[i * lda + c] = x[s][q];
+                }
+            }
+        }
+        __syncthreads();                               // CTA barrier + release store: cumulative, no fence needed
+        if (tid == 0) st_release_gpu_i32(ctrl + e, d);
+    };
+
+    int64_t ev = 0;
+    bool ahead = false;                                // decision of the current row already published (look-ahead)
+    for (int64_t i = 0; i < r; ++i) {
+        const int owner = (int)(i % G), slot = (int)(i / G);
+        const bool mine = cta == owner;
+        int iter = 0;
+        while (true) {
+            int dec;
+            if (i < offset) {
+                dec = GS_FINAL;                        // given orthonormal row, untouched in global memory
+            } else {
+                if (mine && !ahead) decide(i, slot, iter, ev);
+                ahead = false;
+                dec = block_wait_ge(ctrl + ev, 1, timeout_ns, &s_slot);
+                if (dec < 0) {
+                    if (tid == 0) *status = 1;
+                    return;
+                }
+                ++ev;
+            }
+            if (dec == GS_REMOVED) break;
+            double q[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int64_t c = tid + (int64_t)e * nthr;
+                q[e] = c < k ? ldcg_f64(A + i * lda + c) : 0.0;
+            }
+            if (dec == GS_FINAL) {
+                // Look-ahead: the owner of row i+1 completes that row first and publishes its decision
+                // before it updates its other rows, so the chain q_i -> q_{i+1} never waits for
+                // trailing updates.
+                const int64_t i1 = i + 1;
+                int skip = -1;
+                if (i1 < r && i1 >= offset && (int)(i1 % G) == cta) {
+                    const int sl1 = (int)(i1 / G);
+#pragma unroll
+                    for (int s = 0; s < RPC; ++s) {
+                        if (s != sl1 || state[s] != 0) continue;
+                        double p1[1] = {0.0};
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) p1[0] = fma(q[e], x[s][e], p1[0]);
+                        block_sum_n<1>(p1, red);
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) x[s][e] = fma(-p1[0], q[e], x[s][e]);
+                        if (tid == 0) R[i * r + i1] += p1[0];
+                    }
+                    decide(i1, sl1, 0, ev);
+                    ahead = true;
+                    skip = sl1;
+                }
+                // project q_i out of the (other) pending rows this CTA owns
+                double p[RPC];
+                bool any = false;
+#pragma unroll
+                for (int s = 0; s < RPC; ++s) {
+                    const int64_t l = (int64_t)s * G + cta;
+                    p[s] = 0.0;
+                    if (l > i && state[s] == 0 && s != skip) {
+                        any = true;
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) p[s] = fma(q[e], x[s][e], p[s]);
+                    }
+                }
+                if (any) {                             // uniform over the CTA
+                    block_sum_n<RPC>(p, red);
+#pragma unroll
+                    for (int s = 0; s < RPC; ++s) {
+                        const int64_t l = (int64_t)s * G + cta;
+                        if (l > i && state[s] == 0 && s != skip) {
+#pragma unroll
+                            for (int e = 0; e < EPT; ++e) x[s][e] = fma(-p[s], q[e], x[s][e]);
+                            if (tid == 0) R[i * r + l] += p[s];
+                        }
+                    }
+                }
+                break;
+            }
+            // dec == GS_REITER: re-iteration of row i (q holds its current, unnormalised content)
+            {
+                const int64_t e_this = ev - 1;
+                double c_[RPC], v[EPT];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) v[e] = 0.0;
+#pragma unroll
+                for (int s = 0; s < RPC; ++s) {
+                    const int64_t j = (int64_t)s * G + cta;
+                    c_[s] = 0.0;
+                    if (j < i && state[s] == 1) {
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) c_[s] = fma(q[e], x[s][e], c_[s]);
+                    }
+                }
+                block_sum_n<RPC>(c_, red);
+#pragma unroll
+                for (int s = 0; s < RPC; ++s) {
+                    const int64_t j = (int64_t)s * G + cta;
+                    if (j < i) {
+                        if (state[s] == 1) {
+#pragma unroll
+                            for (int e = 0; e < EPT; ++e) v[e] = fma(c_[s], x[s][e], v[e]);
+                        }
+                        if (tid == 0) coef[j] = state[s] == 1 ? c_[s] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int64_t c = tid + (int64_t)e * nthr;
+                    if (c < k) scratch[(int64_t)cta * k + c] = v[e];
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) red_release_gpu_add(done + e_this, 1);
+                if (mine) {
+                    if (block_wait_ge(done + e_this, G, timeout_ns, &s_slot) < 0) {
+                        if (tid == 0) *status = 1;
+                        return;
+                    }
+#pragma unroll
+                    for (int s = 0; s < RPC; ++s) {
+                        if (s != slot) continue;
+                        constexpr int U = EPT <= 4 ? 8 : (EPT <= 8 ? 4 : 2);
+                        for (int g0 = 0; g0 < G; g0 += U) {           // U * EPT loads in flight, summed in CTA order
+                            double t[U][EPT];
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e) {
+                                    const int64_t c = tid + (int64_t)e * nthr;
+                                    t[u][e] = (g0 + u < G && c < k) ? ldcg_f64(scratch + (int64_t)(g0 + u) * k + c) : 0.0;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e) x[s][e] -= t[u][e];
+                            }
+                        }
+                    }
+                    for (int64_t j = tid; j < i; j += nthr) R[j * r + i] += ldcg_f64(coef + j);
+                }
+                ++iter;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ block one-sided Jacobi
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// rotate rows p, q (shared memory) of the sketch part (length k) and of the V part (length m);
+// returns 1 when a rotation was applied.  One warp.
+__device__ __forceinline__ int jacobi_rotate(double *ap, double *aq, int64_t k, double *vp, double *vq, int64_t m,
+                                             double tol) {
+    const int lane = threadIdx.x & 31;
+    double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll 4
+    for (int64_t i = 2 * lane; i < k; i += 64) {       // k is even, rows are 16-byte aligned
+        const double2 x = *reinterpret_cast<const double2 *>(ap + i), y = *reinterpret_cast<const double2 *>(aq + i);
+        a = fma(x.x, x.x, a); b = fma(y.x, y.x, b); g = fma(x.x, y.x, g);
+        a = fma(x.y, x.y, a); b = fma(y.y, y.y, b); g = fma(x.y, y.y, g);
+    }
+    a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+    if (fabs(g) <= tol * sqrt(a * b) || g == 0.0) return 0;
+    const double zeta = (b - a) / (2.0 * g);
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll 4
+    for (int64_t i = 2 * lane; i < k; i += 64) {
+        const double2 x = *reinterpret_cast<const double2 *>(ap + i), y = *reinterpret_cast<const double2 *>(aq + i);
+        *reinterpret_cast<double2 *>(ap + i) = make_double2(c * x.x - s * y.x, c * x.y - s * y.y);
+        *reinterpret_cast<double2 *>(aq + i) = make_double2(s * x.x + c * y.x, s * x.y + c * y.y);
+    }
+    if (vp) {
+#pragma unroll 4
+        for (int64_t i = lane; i < m; i += 32) {
+            const double x = vp[i], y = vq[i];
+            vp[i] = c * x - s * y;
+            vq[i] = s * x + c * y;
+        }
+    }
+    return 1;
+}
+
+// sched: rounds x npairs x 2 block indices over an even number of blocks; (b, -1) marks the bye of
+// block b.  counters: max_sweeps int32, blkflag: one int32 per block, bar: one int32 -- all zero on
+// entry.  info: [0] sweeps done, [1] converged, [2] timeout.
+// Inside a sweep there is NO grid barrier: block b is read and written by exactly one CTA per block
+// round, so its next holder only waits for blkflag[b] (rounds completed on b); one barrier per
+// sweep collects the rotation count.
+template <int B>
+__global__ void __launch_bounds__(32 * B, 1)
+jacobi_block_kernel(double *A, int64_t k, int64_t lda, double *V, int64_t m,
+                    const int32_t *__restrict__ sched, int rounds, double tol, int max_sweeps,
+                    int32_t *counters, double *sval, int32_t *info, int32_t *blkflag, int32_t *bar,
+                    unsigned long long timeout_ns) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_rot, s_slot;
+    const int npairs = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, nthr = blockDim.x;
+    const int64_t ka = k, va = V ? m : 0;
+    const int64_t pitch = (ka + va + 3) & ~int64_t(1); // even: every row stays 16-byte aligned
+    double *rows = sm;                                 // 2B rows: [sketch part (k) | V part (m)]
+    int bar_target = 0;
+
+    if (V) {
+        for (int64_t i = (int64_t)cta * nthr + tid; i < m * m; i += (int64_t)npairs * nthr) V[i] = ((i / m) == (i % m)) ? 1.0 : 0.0;
+        if (grid_barrier(bar, bar_target, npairs, timeout_ns, &s_slot) < 0) {
+            if (tid == 0) info[2] = 1;
+            return;
+        }
+    }
+    // global -> shared with cp.async (16-byte, L2-coherent .cg): every chunk of every row is in flight
+    // at once instead of one L2 round trip per row
+    auto load_block = [&](int blk, int rbase) {
+        const int64_t ca = ka / 2, cv = va / 2;        // 16-byte chunks per row part (k even; m even when V)
+        for (int rr = 0; rr < B; ++rr) {
+            const int64_t g = (int64_t)blk * B + rr;
+            double *dst = rows + (rbase + rr) * pitch;
+            if (g < m) {
+                for (int64_t c = tid; c < ca + cv; c += nthr) {
+                    const double *src = c < ca ? A + g * lda + 2 * c : V + g * m + 2 * (c - ca);
+                    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + 2 * c);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+                }
+            }
+        }
+    };
+    auto load_wait = [&]() {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    };
+    auto store_block = [&](int blk, int rbase) {
+        for (int rr = 0; rr < B; ++rr) {
+            const int64_t g = (int64_t)blk * B + rr;
+            const double *src = rows + (rbase + rr) * pitch;
+            if (g < m) {
+                for (int64_t i = 2 * tid; i < ka; i += 2 * nthr)
+                    *reinterpret_cast<double2 *>(A + g * lda + i) = *reinterpret_cast<const double2 *>(src + i);
+                for (int64_t i = 2 * tid; i < va; i += 2 * nthr)
+                    *reinterpret_cast<double2 *>(V + g * m + i) = *reinterpret_cast<const double2 *>(src + ka + i);
+            }
+        }
+    };
+    // pairs inside block `blk` held at rows [rbase, rbase + B): round-robin over its B rows;
+    // `w0` = first warp working on it, B/2 warps busy per inner round
+    auto intra = [&](int blk, int rbase, int w0, int &rot) {
+        for (int t = 0; t < B - 1; ++t) {
+            const int pi = warp - w0;
+            if (pi >= 0 && pi < B / 2) {
+                const int u = pi == 0 ? 0 : ((pi - 1 + t) % (B - 1)) + 1;
+                const int w = ((B - 2 - pi + t) % (B - 1)) + 1;
+                const int p = min(u, w), q = max(u, w);
+                if ((int64_t)blk * B + q < m) {
+                    double *rp = rows + (rbase + p) * pitch, *rq = rows + (rbase + q) * pitch;
+                    rot += jacobi_rotate(rp, rq, ka, V ? rp + ka : nullptr, V ? rq + ka : nullptr, va, tol);
+                }
+            }
+            __syncthreads();
+        }
+    };
+
+    int sweep = 0, converged = 0, ground = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int rd = 0; rd < rounds; ++rd, ++ground) {
+            const int bx = sched[((int64_t)rd * npairs + cta) * 2], by = sched[((int64_t)rd * npairs + cta) * 2 + 1];
+            if (tid == 0) s_rot = 0;
+            if (bx < 0) continue;                      // (cannot happen with one dummy block at most)
+            // wait until the previous holders of my blocks have written them back
+            if (ground > 0) {
+                if (tid == 0) s_slot = 0;
+                __syncthreads();
+                if (tid == 0 || (tid == 32 && by >= 0)) {            // the two flags are polled concurrently
+                    const int32_t *f = blkflag + (tid == 0 ? bx : by);
+                    const unsigned long long t0 = gtimer_ns();
+                    while (ld_acquire_gpu_i32(f) < ground) {
+                        if (gtimer_ns() - t0 > timeout_ns) { s_slot = -1; break; }
+                    }
+                }
+                __syncthreads();
+                if (s_slot < 0) {
+                    if (tid == 0) info[2] = 1;
+                    return;
+                }
+            }
+            int rot = 0;
+            if (by >= 0) {
+                const int b0 = min(bx, by), b1 = max(bx, by);
+                load_block(b0, 0);
+                load_block(b1, B);
+                load_wait();
+                if (rd == 0 && B > 1) {
+                    // both blocks at once: warps [0, B/2) on b0, [B/2, B) on b1
+                    for (int t = 0; t < B - 1; ++t) {
+                        const int blk = warp / (B / 2), pi = warp % (B / 2);
+                        const int u = pi == 0 ? 0 : ((pi - 1 + t) % (B - 1)) + 1;
+                        const int w = ((B - 2 - pi + t) % (B - 1)) + 1;
+                        const int p = min(u, w), q = max(u, w);
+                        if ((int64_t)(blk ? b1 : b0) * B + q < m) {
+                            double *rp = rows + (blk * B + p) * pitch, *rq = rows + (blk * B + q) * pitch;
+                            rot += jacobi_rotate(rp, rq, ka, V ? rp + ka : nullptr, V ? rq + ka : nullptr, va, tol);
+                        }
+                        __syncthreads();
+                    }
+                }
+                for (int t = 0; t < B; ++t) {
+                    const int p = warp, q = (warp + t) % B;
+                    if ((int64_t)b0 * B + p < m && (int64_t)b1 * B + q < m) {
+                        double *rp = rows + p * pitch, *rq = rows + (B + q) * pitch;
+                        rot += jacobi_rotate(rp, rq, ka, V ? rp + ka : nullptr, V ? rq + ka : nullptr, va, tol);
+                    }
+                    __syncthreads();
+                }
+                store_block(b0, 0);
+                store_block(b1, B);
+            } else if (rd == 0 && B > 1) {
+                // the block that sits out round 0 still gets its inner pairs rotated once per sweep
+                load_block(bx, 0);
+                load_wait();
+                intra(bx, 0, 0, rot);
+                store_block(bx, 0);
+            }
+            if ((tid & 31) == 0 && rot) atomicAdd(&s_rot, rot);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                if (s_rot) atomicAdd(counters + sweep, s_rot);
+                st_release_gpu_i32(blkflag + bx, ground + 1);
+                if (by >= 0) st_release_gpu_i32(blkflag + by, ground + 1);
+            }
+            __syncthreads();
+        }
+        if (grid_barrier(bar, bar_target, npairs, timeout_ns, &s_slot) < 0) {
+            if (tid == 0) info[2] = 1;
+            return;
+        }
+        if (__ldcg(counters + sweep) == 0) { converged = 1; ++sweep; break; }
+    }
+    // singular values: row norms (one warp per row)
+    const int nw = nthr >> 5;
+    for (int64_t g = (int64_t)cta * nw + warp; g < m; g += (int64_t)npairs * nw) {
+        double v = 0.0;
+        for (int64_t i = tid & 31; i < k; i += 32) {
+            const double x = __ldcg(A + g * lda + i);
+            v = fma(x, x, v);
+        }
+        v = warp_sum(v);
+        if ((tid & 31) == 0) sval[g] = sqrt(v);
+    }
+    if (cta == 0 && tid == 0) { info[0] = sweep; info[1] = converged; }
+}
+
+static int coop_ok() {
+    int dev = 0, ok = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&ok, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) return 0;
+    return ok;
+}
+
+struct GsCfg { int rpc, ept, grid; };
+// shape -> kernel configuration, rpc == 0 when the grid kernel does not apply
+static GsCfg gs_config(int64_t r, int64_t k) {
+    GsCfg c = {0, 0, 0};
+    if (r < 16 || k < 1) return c;                      // a handful of rows: the one-CTA kernel is as fast
+    const int sms = sm_count();
+    const int64_t ept = (k + 255) / 256;
+    int rpc = 0, e = 0;
+    if (ept <= 4) { rpc = 8; e = 4; }
+    else if (ept <= 8) { rpc = 8; e = 8; }
+    else if (ept <= 16) { rpc = 4; e = 16; }
+    else return c;
+    const int64_t g = (r + rpc - 1) / rpc;
+    if (g > sms) return c;
+    c.rpc = rpc; c.ept = e; c.grid = (int)g;
+    return c;
+}
+
+}  // namespace rla
+
+using namespace rla;
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct GsLayout { size_t scratch, coef, ctrl, done, status, total; };
+static GsLayout gs_layout(const GsCfg &c, int64_t r, int64_t k) {
+    GsLayout L;
+    const size_t ev = (size_t)(GS_MAX_REITER + 1) * (size_t)r;
+    L.scratch = 0;
+    L.coef = align_up((size_t)c.grid * (size_t)k * sizeof(double), 16);
+    L.ctrl = align_up(L.coef + (size_t)r * sizeof(double), 16);
+    L.done = L.ctrl + ev * sizeof(int32_t);
+    L.status = L.done + ev * sizeof(int32_t);
+    L.total = align_up(L.status + sizeof(int32_t), 16);
+    return L;
+}
+
+extern "C" size_t rla_gram_schmidt_workspace_bytes(int64_t r, int64_t k) {
+    const GsCfg c = gs_config(r, k);
+    if (!c.rpc) return 0;
+    return gs_layout(c, r, k).total;
+}
+
+extern "C" int rla_gram_schmidt_ws_f64(double *a, int64_t r, int64_t k, int64_t lda, int64_t offset, double *R,
+                                       int32_t *flags, double atol, double rtol, double thr, void *ws, size_t ws_bytes,
+                                       void *stream) {
+    const GsCfg c = gs_config(r, k);
+    const size_t need = rla_gram_schmidt_workspace_bytes(r, k);
+    if (!c.rpc || !ws || ws_bytes < need || !coop_ok() || ((uintptr_t)ws & 15))
+        return rla_gram_schmidt_f64(a, r, k, lda, offset, R, flags, atol, rtol, thr, stream);
+    RLA_REQUIRE(lda >= k && offset >= 0, "rla_gram_schmidt_ws_f64: bad sizes");
+    RLA_REQUIRE(a && R && flags, "rla_gram_schmidt_ws_f64: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const GsLayout L = gs_layout(c, r, k);
+    char *base = static_cast<char *>(ws);
+    double *scratch = reinterpret_cast<double *>(base + L.scratch), *coef = reinterpret_cast<double *>(base + L.coef);
+    int32_t *ctrl = reinterpret_cast<int32_t *>(base + L.ctrl), *done = reinterpret_cast<int32_t *>(base + L.done);
+    int32_t *status = reinterpret_cast<int32_t *>(base + L.status);
+    RLA_CUDA_CHECK(cudaMemsetAsync(ctrl, 0, L.total - L.ctrl, st));
+    unsigned long long timeout_ns = 5000000000ull;
+    void *args[] = {&a, &r, &k, &lda, &offset, &R, &flags, &atol, &rtol, &thr, &scratch, &coef, &ctrl, &done, &status,
+                    &timeout_ns};
+    const void *fn = nullptr;
+    if (c.rpc == 8 && c.ept == 4) fn = (const void *)gs_grid_kernel<8, 4>;
+    else if (c.rpc == 8 && c.ept == 8) fn = (const void *)gs_grid_kernel<8, 8>;
+    else fn = (const void *)gs_grid_kernel<4, 16>;
+    // cooperative launch: guarantees that all CTAs are co-resident (they wait on each other's flags)
+    RLA_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(c.grid), dim3(256), args, 0, st));
+    count_launch();
+    return RLA_OK;
+}
+
+// rows per block the block-Jacobi kernel would use for this shape (0: not applicable, use
+// rla_svd_jacobi_f64)
+extern "C" int rla_svd_jacobi_block_rows(int64_t k, int64_t m, int want_v) {
+    if (k < 2 || (k & 1) || m < 4 || (want_v && (m & 1)) || !coop_ok()) return 0;
+    const int sms = sm_count();
+    for (int B = 8; B >= 2; B >>= 1) {
+        const size_t smem = (size_t)2 * B * (size_t)((k + (want_v ? m : 0) + 3) & ~int64_t(1)) * sizeof(double);
+        const int64_t nblk = (m + B - 1) / B;
+        const int64_t npairs = (nblk + 1) / 2;
+        if (smem <= 200 * 1024 && npairs <= sms && nblk >= 2) return B;
+    }
+    return 0;
+}
+
+// scratch_dev: (max_sweeps + ceil(m / B) + 8) int32 (sweep counters, block flags, barrier, info[3])
+extern "C" size_t rla_svd_jacobi_block_scratch_ints(int64_t m, int B, int max_sweeps) {
+    if (B < 1) return 0;
+    return (size_t)max_sweeps + (size_t)((m + B - 1) / B) + 8;
+}
+
+extern "C" int rla_svd_jacobi_block_f64(double *a, int64_t k, int64_t m, int64_t lda, double *s, double *V,
+                                        const int32_t *sched_dev, int B, int32_t *scratch_dev, int max_sweeps,
+                                        double tol, void *stream) {
+    RLA_REQUIRE(a && s && sched_dev && scratch_dev, "rla_svd_jacobi_block_f64: null pointer");
+    RLA_REQUIRE(B == rla_svd_jacobi_block_rows(k, m, V != nullptr) && B >= 2,
+                "rla_svd_jacobi_block_f64: B must be rla_svd_jacobi_block_rows(k, m, want_v)");
+    RLA_REQUIRE(lda >= k && max_sweeps >= 1 && ((uintptr_t)a & 15) == 0 && (lda & 1) == 0,
+                "rla_svd_jacobi_block_f64: bad sizes / alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nblk = (m + B - 1) / B;
+    const int nbe = (int)(nblk + (nblk & 1));
+    int rounds = nbe - 1, npairs = nbe / 2;
+    const size_t smem = (size_t)2 * B * (size_t)((k + (V ? m : 0) + 3) & ~int64_t(1)) * sizeof(double);
+    const size_t ints = rla_svd_jacobi_block_scratch_ints(m, B, max_sweeps);
+    RLA_CUDA_CHECK(cudaMemsetAsync(scratch_dev, 0, sizeof(int32_t) * ints, st));
+    int32_t *info = scratch_dev, *bar = scratch_dev + 4, *counters = scratch_dev + 8, *blkflag = counters + max_sweeps;
+    unsigned long long timeout_ns = 5000000000ull;
+    void *args[] = {&a, &k, &lda, &V, &m, &sched_dev, &rounds, &tol, &max_sweeps, &counters, &s, &info, &blkflag, &bar,
+                    &timeout_ns};
+    const void *fn = B == 8 ? (const void *)jacobi_block_kernel<8>
+                   : B == 4 ? (const void *)jacobi_block_kernel<4> : (const void *)jacobi_block_kernel<2>;
+    RLA_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RLA_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(npairs), dim3(32 * B), args, smem, st));
+    count_launch();
+    return RLA_OK;
+}

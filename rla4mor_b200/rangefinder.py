@@ -41,9 +41,25 @@ def thin_qr(S):
     return ops.gram_schmidt(S)
 
 
-def sketch_svd(S, want_v=True):
-    """SVD of the sketch (see reductor_ops.svd_jacobi)."""
-    return ops.svd_jacobi(S, want_v=want_v)
+def sketch_svd(S, want_v=True, precondition=None, qr=None):
+    """SVD of the k x m sketch held as the row block S (m, k): returns (U_rows (m, k), s (m,),
+    W (m, m) or None) with S = W^T diag(s) U_rows, singular values descending
+    (reductor_ops.svd_jacobi's convention).
+
+    For k >= 2m the Jacobi iteration runs on the m x m triangular factor instead of the m x k
+    sketch (QR preconditioning): S = R^T Q (Gram-Schmidt), R^T = W^T diag(s) Z (block Jacobi on
+    rows of length m), U_rows = Z Q.  Rows four times shorter at BASELINE configs[4]."""
+    m, k = S.shape
+    if precondition is None:
+        precondition = k >= 2 * m and m >= 16
+    if not precondition:
+        return ops.svd_jacobi(S, want_v=want_v)
+    Q, R = ops.gram_schmidt(S) if qr is None else qr    # S = R^T Q, R (m', m) with m' <= m kept rows
+    mk = R.shape[0]
+    M = torch.zeros((m, mk + (mk & 1)), dtype=torch.float64, device=S.device)
+    M[:, :mk] = R.T
+    Z, s, W = ops.svd_jacobi(M, want_v=want_v)
+    return ops.gemm_nn(Z[:, :mk], Q), s, W
 
 
 def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, group=None, svd=True, reducer=None):
@@ -52,6 +68,6 @@ def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, g
     Q, R = thin_qr(S)
     out = {"sketch": S, "Q": Q, "R": R, "T": torch.linalg.pinv(R)}
     if svd:
-        Urows, s, W = sketch_svd(S, want_v=True)
+        Urows, s, W = sketch_svd(S, want_v=True, qr=(Q, R))
         out.update(s=s, W=W, Urows=Urows)
     return out

@@ -67,16 +67,21 @@ def gram_schmidt(A, offset=0, atol=1e-13, rtol=1e-13, reiteration_threshold=9e-1
     if r == 0:
         return A, R
     with torch.cuda.device(A.device):
-        check(lib().rla_gram_schmidt_f64(A.data_ptr(), r, k, A.stride(0), int(offset), R.data_ptr(), flags.data_ptr(),
-                                         float(atol), float(rtol), float(reiteration_threshold), stream_ptr()),
-              "rla_gram_schmidt_f64")
+        # many-CTA grid-synchronised kernel when the shape allows it (csrc/factor.cu), else one CTA
+        ws = dense._workspace(lib().rla_gram_schmidt_workspace_bytes(r, k), A.device)
+        check(lib().rla_gram_schmidt_ws_f64(A.data_ptr(), r, k, A.stride(0), int(offset), R.data_ptr(), flags.data_ptr(),
+                                            float(atol), float(rtol), float(reiteration_threshold),
+                                            ws.data_ptr(), ws.numel(), stream_ptr()),
+              "rla_gram_schmidt_ws_f64")
     keep = flags[:r] == 0
     if not bool(keep.all()):
         A, R = A[keep], R[keep]
     return A, R
 
 
-def _round_robin(m):
+def _round_robin(m, keep_bye=False):
+    """Circle-method schedule over m players (rounded up to even): (me - 1) rounds x (me / 2) pairs.
+    The pair containing the dummy player is (-1, -1), or (p, -1) with keep_bye."""
     me = m + (m & 1)
     players = list(range(me))
     rounds = []
@@ -85,7 +90,7 @@ def _round_robin(m):
         for i in range(me // 2):
             p, q = players[i], players[me - 1 - i]
             if p >= m or q >= m:
-                p, q = -1, -1
+                p, q = (min(p, q), -1) if keep_bye else (-1, -1)
             pairs.append((p, q))
         rounds.append(pairs)
         players = [players[0]] + [players[-1]] + players[1:-1]
@@ -95,7 +100,7 @@ def _round_robin(m):
 _PAIRS = {}
 
 
-def svd_jacobi(S, want_v=False, max_sweeps=30, tol=1e-15):
+def svd_jacobi(S, want_v=False, max_sweeps=30, tol=1e-15, block=True):
     """One-sided Jacobi SVD of the k x m sketch held as a row block S (m, k).
     Returns (U_rows (m, k) orthonormal rows, s (m,), V (m, m) or None), singular values
     sorted descending: S = (V^T diag(s) U_rows) in the row layout, i.e. the k x m matrix
@@ -104,16 +109,33 @@ def svd_jacobi(S, want_v=False, max_sweeps=30, tol=1e-15):
     m, k = A.shape
     s = torch.empty((m,), dtype=torch.float64, device=A.device)
     V = torch.empty((m, m), dtype=torch.float64, device=A.device) if want_v else None
-    key = (m, A.device.index)
-    if key not in _PAIRS:
-        _PAIRS[key] = torch.from_numpy(_round_robin(m)).to(A.device)
-    rot = torch.zeros((1,), dtype=torch.int32, device=A.device)
-    done = ctypes.c_int(0)
-    with torch.cuda.device(A.device):
-        check(lib().rla_svd_jacobi_f64(A.data_ptr(), k, m, A.stride(0), s.data_ptr(),
-                                       V.data_ptr() if want_v else None, _PAIRS[key].data_ptr(), rot.data_ptr(),
-                                       int(max_sweeps), float(tol), ctypes.byref(done), stream_ptr()),
-              "rla_svd_jacobi_f64")
+    B = lib().rla_svd_jacobi_block_rows(k, m, 1 if want_v else 0) if (block and A.data_ptr() % 16 == 0
+                                                                       and A.stride(0) % 2 == 0) else 0
+    if B:
+        # one persistent launch: block pairs in shared memory, grid barrier per block round (csrc/factor.cu)
+        nblk = -(-m // B)
+        key = ("blk", nblk, A.device.index)
+        if key not in _PAIRS:
+            _PAIRS[key] = torch.from_numpy(_round_robin(nblk, keep_bye=True)).to(A.device)
+        scratch = torch.empty((lib().rla_svd_jacobi_block_scratch_ints(m, B, int(max_sweeps)),), dtype=torch.int32,
+                              device=A.device)
+        with torch.cuda.device(A.device):
+            check(lib().rla_svd_jacobi_block_f64(A.data_ptr(), k, m, A.stride(0), s.data_ptr(),
+                                                 V.data_ptr() if want_v else None, _PAIRS[key].data_ptr(), B,
+                                                 scratch.data_ptr(), int(max_sweeps), float(tol), stream_ptr()),
+                  "rla_svd_jacobi_block_f64")
+        svd_jacobi.last_info = scratch[:3]              # {sweeps, converged, timeout} (device; read lazily)
+    else:
+        key = (m, A.device.index)
+        if key not in _PAIRS:
+            _PAIRS[key] = torch.from_numpy(_round_robin(m)).to(A.device)
+        rot = torch.zeros((1,), dtype=torch.int32, device=A.device)
+        done = ctypes.c_int(0)
+        with torch.cuda.device(A.device):
+            check(lib().rla_svd_jacobi_f64(A.data_ptr(), k, m, A.stride(0), s.data_ptr(),
+                                           V.data_ptr() if want_v else None, _PAIRS[key].data_ptr(), rot.data_ptr(),
+                                           int(max_sweeps), float(tol), ctypes.byref(done), stream_ptr()),
+                  "rla_svd_jacobi_f64")
     order = torch.argsort(s, descending=True)
     s = s[order]
     A = A[order]

@@ -55,7 +55,7 @@ def test_spmm_and_gemm_nn_and_gram(rb):
     assert rel_fro(ops.gram(_dev(a), _dev(b)).cpu().numpy(), a @ b.T) < 1e-12
 
 
-@pytest.mark.parametrize("r,k", [(6, 40), (20, 1000), (64, 4000), (3, 5000)])
+@pytest.mark.parametrize("r,k", [(6, 40), (20, 1000), (64, 4000), (3, 5000), (100, 2000), (256, 1024), (17, 33)])
 def test_gram_schmidt_matches_oracle(rb, r, k):
     from rla4mor_b200 import reductor_ops as ops
     A = np.random.RandomState(r).standard_normal((r, k))
@@ -72,7 +72,7 @@ def test_gram_schmidt_matches_oracle(rb, r, k):
     assert rel_fro(Q2.cpu().numpy(), Qo2) < 1e-10 and rel_fro(R2.cpu().numpy(), Ro2) < 1e-10
 
 
-@pytest.mark.parametrize("m,k", [(5, 40), (32, 600), (64, 1024), (33, 500)])
+@pytest.mark.parametrize("m,k", [(5, 40), (32, 600), (64, 1024), (33, 500), (256, 1024), (21, 501), (130, 258)])
 def test_jacobi_svd(rb, m, k):
     from rla4mor_b200 import reductor_ops as ops
     S = np.random.RandomState(m).standard_normal((m, k)) * np.logspace(0, -6, m)[:, None]
@@ -82,6 +82,65 @@ def test_jacobi_svd(rb, m, k):
     rec = (V.T * s) @ U                                          # S = V^T diag(s) U_rows
     assert rel_fro(rec.cpu().numpy(), S) < 1e-12
     assert rel_fro((U @ U.T).cpu().numpy(), np.eye(m)) < 1e-10
+
+
+def test_gram_schmidt_grid_kernel_semantics(rb):
+    """The many-CTA kernel (csrc/factor.cu) keeps pyMOR's semantics: removal of dependent rows,
+    zero rows, re-iteration, and agrees with the one-CTA kernel it replaces."""
+    from rla4mor_b200 import reductor_ops as ops
+    import torch
+    rs = np.random.RandomState(7)
+    r, k = 96, 700
+    base = rs.standard_normal((40, k))
+    base[10] = 0.0                                                         # a zero row
+    A = np.vstack([base, rs.standard_normal((56, 40)) @ base * 1.0])     # rows 40.. are dependent on the first 40
+    A[50] = rs.standard_normal(k)                                          # except these two
+    A[77] = rs.standard_normal(k)
+    assert rb.lib().rla_gram_schmidt_workspace_bytes(r, k) > 0            # the grid kernel applies
+    Qd, Rd = ops.gram_schmidt(_dev(A))
+    Qo, Ro = ro.gram_schmidt(A)
+    assert Qd.shape == Qo.shape == (41, k) and Rd.shape == Ro.shape
+    assert rel_fro((Qd @ Qd.T).cpu().numpy(), np.eye(41)) < 1e-12
+    assert rel_fro(Rd.cpu().numpy(), Ro) < 1e-9 and rel_fro(Qd.cpu().numpy(), Qo) < 1e-8
+    # same answer as the one-CTA kernel on a well-conditioned block (both follow the same recurrence)
+    B = rs.standard_normal((200, 900))
+    Q1, R1 = ops.gram_schmidt(_dev(B))
+    Bd = _dev(B).clone()
+    R2 = torch.empty((200, 200), dtype=torch.float64, device="cuda")
+    fl = torch.empty((200,), dtype=torch.int32, device="cuda")
+    rb._lib.check(rb.lib().rla_gram_schmidt_f64(Bd.data_ptr(), 200, 900, 900, 0, R2.data_ptr(), fl.data_ptr(),
+                                                1e-13, 1e-13, 0.9, rb._lib.stream_ptr()), "gs")
+    assert int(fl.sum()) == 0
+    assert rel_fro(Q1.cpu().numpy(), Bd.cpu().numpy()) < 1e-12 and rel_fro(R1.cpu().numpy(), R2.cpu().numpy()) < 1e-13
+    assert rel_fro((R1.T @ Q1).cpu().numpy(), B) < 1e-13                  # A = R^T Q
+
+
+def test_jacobi_block_vs_round_kernel(rb):
+    from rla4mor_b200 import reductor_ops as ops
+    S = np.random.RandomState(11).standard_normal((70, 512)) * np.logspace(0, -9, 70)[:, None]
+    U1, s1, V1 = ops.svd_jacobi(_dev(S), want_v=True)
+    U2, s2, V2 = ops.svd_jacobi(_dev(S), want_v=True, block=False)
+    s_ref = np.linalg.svd(S, compute_uv=False)
+    assert np.max(np.abs(s1.cpu().numpy() - s_ref) / s_ref) < 1e-9        # high RELATIVE accuracy (Jacobi)
+    assert np.max(np.abs(s2.cpu().numpy() - s_ref) / s_ref) < 1e-9
+    assert rel_fro(((V1.T * s1) @ U1).cpu().numpy(), S) < 1e-12
+    U3, s3, _ = ops.svd_jacobi(_dev(S), want_v=False)
+    assert np.max(np.abs(s3.cpu().numpy() - s_ref) / s_ref) < 1e-9
+
+
+def test_sketch_svd_qr_preconditioned(rb):
+    from rla4mor_b200.rangefinder import sketch_svd
+    rs = np.random.RandomState(5)
+    for m, k, decay in ((64, 512, -6), (37, 300, -3), (48, 400, -18)):   # last one: numerically rank deficient
+        S = rs.standard_normal((m, m)) @ (np.logspace(0, decay, m)[:, None] * rs.standard_normal((m, k)))
+        U, s, W = sketch_svd(_dev(S), want_v=True, precondition=True)
+        s_ref = np.linalg.svd(S, compute_uv=False)
+        assert np.max(np.abs(s.cpu().numpy() - s_ref)) / s_ref[0] < 1e-12
+        rec = (W.T * s) @ U
+        assert rel_fro(rec.cpu().numpy(), S) < 1e-11
+        r_num = int((s_ref > 1e-10 * s_ref[0]).sum())
+        Un = U[:r_num].cpu().numpy()
+        assert rel_fro(Un @ Un.T, np.eye(r_num)) < 1e-6
 
 
 def test_residual_norm(rb):

@@ -112,7 +112,15 @@ def run_c5(rank, world, dev, steps=10, warmup=3, hbm_peak=None, dmma_peak=None):
     t_qr, _ = timed(lambda: rangefinder.thin_qr(S), max(2, steps // 2), 1)
     t_svd, _ = timed(lambda: rangefinder.sketch_svd(S), max(2, steps // 2), 1)
     t_gs, _ = timed(lambda: ops.gram_schmidt(S), 2, 1)
-    out["factorisation"] = {"thin_qr_ms": t_qr, "svd_ms": t_svd, "gram_schmidt_pymor_semantics_ms": t_gs}
+    t_svd_direct, _ = timed(lambda: ops.svd_jacobi(S, want_v=True), 2, 1)
+    info_direct = [int(v) for v in ops.svd_jacobi.last_info.tolist()] if hasattr(ops.svd_jacobi, "last_info") else None
+    rangefinder.sketch_svd(S)
+    info_pre = [int(v) for v in ops.svd_jacobi.last_info.tolist()] if hasattr(ops.svd_jacobi, "last_info") else None
+    t_svd_old, _ = timed(lambda: ops.svd_jacobi(S, want_v=True, block=False), 2, 1)
+    out["factorisation"] = {"thin_qr_ms": t_qr, "svd_ms": t_svd, "gram_schmidt_pymor_semantics_ms": t_gs,
+                            "svd_block_jacobi_direct_ms": t_svd_direct, "svd_round_per_launch_ms": t_svd_old,
+                            "block_jacobi_info_direct(sweeps,converged,timeout)": info_direct,
+                            "block_jacobi_info_preconditioned": info_pre}
     # whole range finder step, SRHT when the world size allows it
     kind = "srht" if "srht" in out else "gauss"
     t_all, l_all = timed(lambda: rangefinder.sketched_range_finder(U, n, K, 0, kind, rank, world, reducer=reducer),
