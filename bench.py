@@ -12,8 +12,12 @@ A step is one pass of the hot path over one block of synthetic vectors.  Workloa
     srht_c3             SRHT k=4000 on a float64 2^24 x 1024 block, column-sharded
                         (configs[2]; HBM bound); run as the `secondary` result
     srht_c1             SRHT k=1000 on 2^16 x 200 (configs[0], the reference's CPU case)
+    rangefinder_c5      sketch + thin QR / SVD of a 2^23 x 256 block, k=1024, ROW-sharded with one
+                        exchange of the (m, k) partials over NVLink peer memory (configs[4]);
+                        second `secondary` result (tools/bench_c5.py)
 Multi-GPU: column-sharded, no collective.  gauss_c2 scales weakly (every rank sketches its
-own 2^22 x 512 block); srht_c3 is the fixed 2^24 x 1024 block split by columns (strong).
+own 2^22 x 512 block); srht_c3 is the fixed 2^24 x 1024 block split by columns (strong);
+rangefinder_c5 is the fixed block split by rows (strong).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -317,7 +321,7 @@ def run_ours(args):
         roof.update(achieved=achieved, frac=achieved / roof["peak"], traffic=traffic,
                     achieved_best_step=work / best / (1e12 if roof["bound"] == "tensor" else 1e9),
                     step_ms=[round(v, 3) for v in timed.last_step_ms],
-                    kernel="sketch_gemm_kernel" if wl["kind"] == "gauss" else "srht_main_kernel",
+                    kernel="sketch_gemm_kernel" if wl["kind"] == "gauss" else "srht_ws_kernel",
                     note="duration = whole step (main kernel + its small reduce/finalize kernel), CUDA events")
         res = {
             "workload": name, "value": m_total * n * 8 / t_step / 1e9, "unit": "GB/s",
@@ -362,6 +366,16 @@ def run_ours(args):
     if not args.no_secondary and args.workload == "gauss_c2":
         secondary.append(run_workload("srht_c3", False, False, max(3, min(args.steps, 10)), max(3, args.warmup)))
         secondary[-1].pop("_host_block", None)
+
+    if not args.no_secondary and args.workload == "gauss_c2":
+        # configs[4]: row-sharded range finder (sketch + NVLink peer-memory exchange + thin QR / SVD)
+        try:
+            from tools.bench_c5 import run_c5
+            pk = primary["roofline"].get("peak") if primary["roofline"]["bound"] == "tensor" else None
+            secondary.append(run_c5(rank, world, dev, steps=max(3, min(args.steps, 10)), warmup=3,
+                                    hbm_peak=float(peaks["hbm_gbs"]), dmma_peak=pk))
+        except Exception as exc:                                       # never lose the primary line to a secondary
+            secondary.append({"workload": "rangefinder_c5", "error": f"{type(exc).__name__}: {exc}"[:300]})
 
     cpu = None
     if rank == 0 and world >= 1 and not args.no_cpu_baseline and args.gpus == 1:

@@ -213,6 +213,10 @@ int rla_svd_jacobi_block_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
                              double *s_dev, double *V_dev, const int32_t *sched_dev, int B,
                              int32_t *scratch_dev, int max_sweeps, double tol, void *stream);
 
+/* T = R^-1 for the upper-triangular r x r factor of Gram-Schmidt (row-major): the reference's
+ * T = pinv(R) (mor/sketched_reductor.py:95) when no row was removed. */
+int rla_trinv_upper_f64(const double *R_dev, int64_t r, int64_t ldr, double *T_dev, int64_t ldt, void *stream);
+
 /* Sketched residual norm  || sum_q th[q] S_q a - sum_p tr[p] b_p ||_2
  * (ResidualErrorEstimator.estimate_error, mor/sketched_reductor.py:216-219);
  * S_dev is Q contiguous k x r row-major blocks, b_dev P contiguous k-vectors. */
@@ -220,6 +224,44 @@ int rla_residual_norm_f64(const double *S_dev, int64_t Q, int64_t k, int64_t r,
                           const double *th_dev, const double *a_dev,
                           const double *b_dev, int64_t P, const double *tr_dev,
                           double *out_dev, void *stream);
+
+/* --------------------------------------- sparse triangular solves (8f.1) ----
+ * Device side of InverseLuOperator.apply / apply_adjoint (utilities/factorization.py:118-132,
+ * `slu.solve(V.T).T`): the inverse_product R^-1 in front of the sketch
+ * (mor/sketched_reductor.py:69,73).  The factorisation Pr A Pc = L U is SciPy SuperLU's, on the
+ * host, as in the reference; L and U are uploaded as CSR.
+ * rla_sptrsv_plan_host (HOST arrays in and out, plain C++ on the CPU, once per factor): level of
+ * every row (lower != 0: dependencies j < i; else j > i), rows sorted by level (order_out, inverse
+ * pos_out), the strictly triangular part re-packed as CSR with the entries of a row sorted by the
+ * position of their column (rowptr2 n + 1, col2 / val2 up to nnz), the diagonal (1.0 where absent)
+ * and the step list: step s covers order positions [step_lo[s], step_hi[s]); kind 0 = one level
+ * of more than `narrow` independent rows, kind 1 = a group of at most group_rows (<= 32) rows cut
+ * from a run of narrow levels; split_out[i] = first entry of row i that refers to a row of its
+ * own group (for those entries col2 holds the slot inside the group).  step arrays: n entries.
+ * rla_sptrsv_transpose_in/out: (m, n) block of the reference layout <-> X (n, ldx) with the m
+ * right-hand sides contiguous (ldx even, >= m), with the row / column permutation of the
+ * factorisation applied on the way (perm_dev may be NULL): X[perm[i], c] = B[c, i] and
+ * out[c, i] = X[perm[i], c].
+ * rla_sptrsv_solve_f64: in-place T X = X, one launch per step (the step arrays stay on the
+ * HOST); diag_dev NULL = unit diagonal; scratch_dev: rla_sptrsv_scratch_bytes(ldx) bytes,
+ * zero-filled once by the caller. */
+int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val,
+                         int lower, int narrow, int group_rows,
+                         int32_t *level_out, int32_t *order_out, int32_t *pos_out,
+                         int64_t *rowptr2, int32_t *col2, double *val2, double *diag_out,
+                         int64_t *split_out, int64_t *step_lo, int64_t *step_hi, int32_t *step_kind,
+                         int64_t *nsteps_out, int32_t *nlevels_out);
+int rla_sptrsv_transpose_in_f64(const double *b_dev, int64_t m, int64_t n, int64_t ldb,
+                                const int32_t *perm_dev, double *x_dev, int64_t ldx, void *stream);
+int rla_sptrsv_transpose_out_f64(const double *x_dev, int64_t m, int64_t n, int64_t ldx,
+                                 const int32_t *perm_dev, double *out_dev, int64_t ldo, void *stream);
+size_t rla_sptrsv_scratch_bytes(int64_t ldx);
+int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *col_dev, const double *val_dev,
+                         const double *diag_dev, const int32_t *order_dev, const int32_t *pos_dev,
+                         const int64_t *split_dev,
+                         const int64_t *step_lo_host, const int64_t *step_hi_host, const int32_t *step_kind_host,
+                         int64_t nsteps, double *x_dev, int64_t m, int64_t ldx,
+                         void *scratch_dev, size_t scratch_bytes, void *stream);
 
 /* ------------------------------------------- row-sharded exchange (K5) -----
  * The one exchange step of the row-sharded sketch (no reference

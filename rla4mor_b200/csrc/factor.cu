@@ -539,6 +539,29 @@ jacobi_block_kernel(double *A, int64_t k, int64_t lda, double *V, int64_t m,
     if (cta == 0 && tid == 0) { info[0] = sweep; info[1] = converged; }
 }
 
+// ------------------------------------------------------------------ T = R^-1, R upper triangular
+// (the reference's T = pinv(R) for the square, full-rank R of Gram-Schmidt, mor/sketched_reductor.py:95)
+// One warp per column j of T: back substitution R t = e_j, the inner sum split over the lanes.
+__global__ void __launch_bounds__(128)
+trinv_upper_kernel(const double *__restrict__ R, int64_t r, int64_t ldr, double *__restrict__ T, int64_t ldt) {
+    extern __shared__ double tsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * 4 + warp;
+    if (j >= r) return;
+    double *t = tsm + (int64_t)warp * r;
+    for (int64_t i = j + 1 + lane; i < r; i += 32) T[i * ldt + j] = 0.0;
+    if (lane == 0) t[j] = 1.0 / R[j * ldr + j];
+    __syncwarp();
+    for (int64_t i = j - 1; i >= 0; --i) {
+        double acc = 0.0;
+        for (int64_t l = i + 1 + lane; l <= j; l += 32) acc = fma(R[i * ldr + l], t[l], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) t[i] = -acc / R[i * ldr + i];
+        __syncwarp();
+    }
+    for (int64_t i = lane; i <= j; i += 32) T[i * ldt + j] = t[i];
+}
+
 static int coop_ok() {
     int dev = 0, ok = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -662,5 +685,18 @@ extern "C" int rla_svd_jacobi_block_f64(double *a, int64_t k, int64_t m, int64_t
     RLA_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RLA_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(npairs), dim3(32 * B), args, smem, st));
     count_launch();
+    return RLA_OK;
+}
+
+extern "C" int rla_trinv_upper_f64(const double *R, int64_t r, int64_t ldr, double *T, int64_t ldt, void *stream) {
+    RLA_REQUIRE(r >= 0 && ldr >= r && ldt >= r, "rla_trinv_upper_f64: bad sizes");
+    if (r == 0) return RLA_OK;
+    RLA_REQUIRE(R && T, "rla_trinv_upper_f64: null pointer");
+    RLA_REQUIRE(r <= 6144, "rla_trinv_upper_f64: r=%lld > 6144", (long long)r);
+    const size_t smem = (size_t)4 * (size_t)r * sizeof(double);
+    RLA_CUDA_CHECK(cudaFuncSetAttribute((const void *)trinv_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trinv_upper_kernel<<<(unsigned)((r + 3) / 4), 128, smem, (cudaStream_t)stream>>>(R, r, ldr, T, ldt);
+    count_launch();
+    RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;
 }

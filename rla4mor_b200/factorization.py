@@ -1,0 +1,204 @@
+"""B200 counterpart of the reference's `utilities/factorization.py` for the step in front of the
+sketch: `InverseLuOperator` -- the `inverse_product` R^-1 of
+`SketchedReductor` (mor/sketched_reductor.py:69,73) -- and the Cholesky-type `sqrt_product` Q of
+the embeddings (`lu_to_cholesky`, `operator_to_cholesky`).
+
+As in the reference the sparse LU FACTORISATION is SciPy SuperLU's on the host
+(factorization.py:17-22,115); what moves to the GPU is every application: the two sparse
+triangular solves of `slu.solve(V.T).T` (:118-132) over the whole block of vectors
+(csrc/sptrsv.cu), and Q as a CSR SpMM (vectorarray.MatrixOperator).  Same class / function names
+and constructor arguments as the reference.  Real matrices only.
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import check, lib, require_cuda, stream_ptr
+from .vectorarray import DeviceVectorArray, DeviceVectorSpace, MatrixOperator
+
+
+def splu_symetric(matrix):
+    """factorization.py:17-22."""
+    from scipy.sparse.linalg import splu
+    return splu(matrix, permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0, options={'SymmetricMode': True})
+
+
+def lu_to_cholesky(matrix=None, factor=None):
+    """factorization.py:24-52: Q with Q^H Q == matrix from the symmetric-mode LU (host, SciPy)."""
+    from scipy.sparse import csc_matrix, diags
+    if factor is None:
+        assert not (matrix is None)
+        factor = splu_symetric(matrix)
+    n = factor.perm_c.shape[0]
+    P = csc_matrix((np.ones(n), (factor.perm_r, np.arange(n))))
+    D = diags(factor.U.diagonal() ** 0.5)
+    return (P.T @ factor.L @ D).conj().T
+
+
+def operator_to_cholesky(operator=None, factor=None):
+    """factorization.py:55-81: the Cholesky factor as a (device CSR) matrix operator."""
+    try:
+        matrix, source_id, range_id = operator._host, operator.source.id, operator.range.id
+    except AttributeError:
+        matrix, source_id, range_id = None, None, None
+    if matrix is not None:
+        matrix = matrix.tocsc()
+    M = lu_to_cholesky(matrix, factor)
+    return MatrixOperator(M, source_id, range_id)
+
+
+def plan_triangular(T, lower, narrow=32, group=32):
+    """Host analysis of one triangular factor (C++ in librla_b200.so, no GPU involved): dict of
+    NumPy arrays -- see rla_sptrsv_plan_host in include/rla_b200.h."""
+    T = T.tocsr()
+    n = T.shape[0]
+    rowptr = np.ascontiguousarray(T.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(T.indices, dtype=np.int32)
+    val = np.ascontiguousarray(T.data, dtype=np.float64)
+    nnz = int(T.nnz)
+    level, order, pos = (np.empty(max(n, 1), dtype=np.int32) for _ in range(3))
+    rowptr2 = np.empty(n + 1, dtype=np.int64)
+    col2, val2 = np.empty(max(nnz, 1), dtype=np.int32), np.empty(max(nnz, 1), dtype=np.float64)
+    diag, split = np.empty(max(n, 1), dtype=np.float64), np.empty(max(n, 1), dtype=np.int64)
+    step_lo, step_hi = np.empty(max(n, 1), dtype=np.int64), np.empty(max(n, 1), dtype=np.int64)
+    step_kind = np.empty(max(n, 1), dtype=np.int32)
+    nsteps, nlev = ctypes.c_int64(0), ctypes.c_int32(0)
+    check(lib().rla_sptrsv_plan_host(n, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, 1 if lower else 0,
+                                     int(narrow), int(group), level.ctypes.data, order.ctypes.data, pos.ctypes.data,
+                                     rowptr2.ctypes.data, col2.ctypes.data, val2.ctypes.data, diag.ctypes.data,
+                                     split.ctypes.data, step_lo.ctypes.data, step_hi.ctypes.data,
+                                     step_kind.ctypes.data, ctypes.byref(nsteps), ctypes.byref(nlev)),
+          "rla_sptrsv_plan_host")
+    ns, nz = int(nsteps.value), int(rowptr2[n])
+    return dict(n=n, nlevels=int(nlev.value), nsteps=ns, level=level[:n], order=order[:n], pos=pos[:n],
+                rowptr=rowptr2, col=col2[:max(nz, 1)], val=val2[:max(nz, 1)], nnz=nz, diag=diag[:n], split=split[:n],
+                step_lo=np.ascontiguousarray(step_lo[:ns]), step_hi=np.ascontiguousarray(step_hi[:ns]),
+                step_kind=np.ascontiguousarray(step_kind[:ns]))
+
+
+class TriangularFactor:
+    """One triangular CSR matrix on the device with its schedule (levels, rows sorted by level,
+    groups of the narrow tail: plan_triangular)."""
+
+    NARROW = 32          # levels of at most this many rows are cut into groups
+    GROUP = 32
+
+    def __init__(self, T, lower, unit_diagonal, device):
+        torch = require_cuda()
+        p = plan_triangular(T, lower, self.NARROW, self.GROUP)
+        self.n, self.lower = p["n"], bool(lower)
+        self.nlevels, self.nsteps, self.nnz = p["nlevels"], p["nsteps"], p["nnz"]
+        self.step_lo, self.step_hi, self.step_kind = p["step_lo"], p["step_hi"], p["step_kind"]
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.rowptr, self.col, self.val = dev(p["rowptr"]), dev(p["col"]), dev(p["val"])
+        self.diag = None if unit_diagonal else dev(p["diag"])
+        self.order, self.pos, self.split = dev(p["order"]), dev(p["pos"]), dev(p["split"])
+        self._scratch = {}
+
+    def solve_inplace(self, X, m):
+        """T X = X on the (n, ldx) device block with the m right-hand sides contiguous."""
+        import torch
+        ldx = X.stride(0)
+        key = (ldx, X.device.index)
+        if key not in self._scratch:
+            self._scratch[key] = torch.zeros(lib().rla_sptrsv_scratch_bytes(ldx), dtype=torch.uint8, device=X.device)
+        sc = self._scratch[key]
+        check(lib().rla_sptrsv_solve_f64(self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
+                                         None if self.diag is None else self.diag.data_ptr(), self.order.data_ptr(),
+                                         self.pos.data_ptr(), self.split.data_ptr(), self.step_lo.ctypes.data,
+                                         self.step_hi.ctypes.data, self.step_kind.ctypes.data, self.nsteps,
+                                         X.data_ptr(), int(m), ldx, sc.data_ptr(), sc.numel(), stream_ptr()),
+              "rla_sptrsv_solve_f64")
+        return X
+
+
+class SparseLU:
+    """Device image of a SciPy SuperLU factorisation  Pr A Pc = L U  (real)."""
+
+    def __init__(self, factorization, device=None):
+        torch = require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n = int(factorization.shape[0])
+        L, U = factorization.L, factorization.U
+        assert not np.iscomplexobj(L.data) and not np.iscomplexobj(U.data), "real factorisations only"
+        self._L, self._U = L.tocsr(), U.tocsr()
+        self.perm_r = torch.from_numpy(np.ascontiguousarray(factorization.perm_r, dtype=np.int32)).to(self.device)
+        self.perm_c = torch.from_numpy(np.ascontiguousarray(factorization.perm_c, dtype=np.int32)).to(self.device)
+        self._fwd = None
+        self._adj = None
+
+    def _factors(self, adjoint):
+        if not adjoint:
+            if self._fwd is None:
+                self._fwd = (TriangularFactor(self._L, True, True, self.device),
+                             TriangularFactor(self._U, False, False, self.device))
+            return self._fwd
+        if self._adj is None:
+            self._adj = (TriangularFactor(self._U.T.tocsr(), True, False, self.device),
+                         TriangularFactor(self._L.T.tocsr(), False, True, self.device))
+        return self._adj
+
+    def solve(self, B, adjoint=False):
+        """(m, n) block of right-hand sides (one per row) -> (m, n) block of solutions of
+        A x = b (or A^H x = b): what `slu.solve(V.T[, trans='H']).T` computes."""
+        import torch
+        assert B.is_cuda and B.dim() == 2 and B.shape[1] == self.n
+        B = B.to(torch.float64)
+        if B.stride(1) != 1:
+            B = B.contiguous()
+        m = B.shape[0]
+        out = torch.empty((m, self.n), dtype=torch.float64, device=B.device)
+        if m == 0 or self.n == 0:
+            return out
+        first, second = self._factors(adjoint)
+        p_in, p_out = (self.perm_c, self.perm_r) if adjoint else (self.perm_r, self.perm_c)
+        ldx = m + (m & 1)
+        with torch.cuda.device(B.device):
+            X = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
+            check(lib().rla_sptrsv_transpose_in_f64(B.data_ptr(), m, self.n, B.stride(0), p_in.data_ptr(),
+                                                    X.data_ptr(), ldx, stream_ptr()), "rla_sptrsv_transpose_in_f64")
+            first.solve_inplace(X, m)
+            second.solve_inplace(X, m)
+            check(lib().rla_sptrsv_transpose_out_f64(X.data_ptr(), m, self.n, ldx, p_out.data_ptr(),
+                                                     out.data_ptr(), out.stride(0), stream_ptr()),
+                  "rla_sptrsv_transpose_out_f64")
+        return out
+
+
+class InverseLuOperator:
+    """Implicit inverse of a sparse matrix through its LU factorisation
+    (factorization.py:84-138): `apply` solves with the factors, `apply_inverse` applies the
+    matrix.  Factorisation on the host (SciPy SuperLU, as the reference), solves on the GPU."""
+    linear = True
+
+    def __init__(self, operator, factorization=None, symetric=False, splu_kwargs=None):
+        from scipy.sparse.linalg import splu
+        self.operator = operator
+        self.source = operator.range
+        self.range = operator.source
+        self.symetric = symetric
+        if splu_kwargs is None:
+            splu_kwargs = dict()
+        self.splu_kwargs = splu_kwargs
+        if factorization is None:
+            matrix = operator._host.tocsc()
+            if symetric:
+                factorization = splu_symetric(matrix)                    # :113-114
+            else:
+                factorization = splu(matrix, **splu_kwargs)              # :115-116
+        self.factorization = factorization
+        self._device_lu = SparseLU(factorization)
+
+    def apply(self, U, mu=None):                                         # :118-124
+        assert U in self.source
+        return DeviceVectorArray(self.source, self._device_lu.solve(U.data))
+
+    def apply_adjoint(self, U, mu=None):                                 # :126-132
+        assert U in self.source
+        return DeviceVectorArray(self.source, self._device_lu.solve(U.data, adjoint=True))
+
+    def apply_inverse(self, U, mu=None):                                 # :134-135
+        return self.operator.apply(U)
+
+    def apply_inverse_adjoint(self, U, mu=None):                         # :137-138
+        return self.operator.apply_adjoint(U)

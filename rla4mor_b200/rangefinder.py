@@ -66,7 +66,7 @@ def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, g
     """Returns dict(sketch, Q, R, T[, s, W]) -- all small (m x k, m x m) device tensors."""
     S = sketch_block(U_local, n, k, seed, kind, rank, world, group, reducer)
     Q, R = thin_qr(S)
-    out = {"sketch": S, "Q": Q, "R": R, "T": torch.linalg.pinv(R)}
+    out = {"sketch": S, "Q": Q, "R": R, "T": ops.pinv_R(R)}
     if svd:
         Urows, s, W = sketch_svd(S, want_v=True, qr=(Q, R))
         out.update(s=s, W=W, Urows=Urows)

@@ -79,6 +79,23 @@ def gram_schmidt(A, offset=0, atol=1e-13, rtol=1e-13, reiteration_threshold=9e-1
     return A, R
 
 
+def pinv_R(R):
+    """T = pinv(R) of the Gram-Schmidt factor (mor/sketched_reductor.py:95).  A square R (no row
+    removed) is upper triangular with a positive diagonal: T = R^-1 by back substitution on the
+    device; a rectangular R (rows removed) goes through the general pseudo-inverse."""
+    if R.shape[0] != R.shape[1]:
+        return torch.linalg.pinv(R)
+    R = _rows(R).to(torch.float64)
+    r = R.shape[0]
+    T = torch.empty((r, r), dtype=torch.float64, device=R.device)
+    if r == 0:
+        return T
+    with torch.cuda.device(R.device):
+        check(lib().rla_trinv_upper_f64(R.data_ptr(), r, R.stride(0), T.data_ptr(), T.stride(0), stream_ptr()),
+              "rla_trinv_upper_f64")
+    return T
+
+
 def _round_robin(m, keep_bye=False):
     """Circle-method schedule over m players (rounded up to even): (me - 1) rounds x (me / 2) pairs.
     The pair containing the dummy player is (-1, -1), or (p, -1) with keep_bye."""

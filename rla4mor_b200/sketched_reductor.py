@@ -76,7 +76,7 @@ class SketchedReductor:
     def orthonormalize_basis(self, offset=0, T=None):                    # :90-118
         if T is None:
             Q, R = ops.gram_schmidt(self.srb, offset=offset)             # :94
-            T = torch.linalg.pinv(R)                                     # :95  (r x r, host-sized)
+            T = ops.pinv_R(R)                                            # :95  (r x r)
         else:
             T = torch.as_tensor(T, dtype=torch.float64, device=self.srb.device)
             Q = ops.gemm_nn(T.T.contiguous(), self.srb)                  # :97

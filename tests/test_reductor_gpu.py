@@ -143,6 +143,16 @@ def test_sketch_svd_qr_preconditioned(rb):
         assert rel_fro(Un @ Un.T, np.eye(r_num)) < 1e-6
 
 
+def test_pinv_R_triangular_inverse(rb):
+    from rla4mor_b200 import reductor_ops as ops
+    for r in (1, 5, 64, 257):
+        R = np.triu(np.random.RandomState(r).standard_normal((r, r))) + 3.0 * np.eye(r)
+        T = ops.pinv_R(_dev(R)).cpu().numpy()
+        assert rel_fro(T, np.linalg.inv(R)) < 1e-12 and np.all(np.tril(T, -1) == 0.0)
+    Rr = np.random.RandomState(0).standard_normal((3, 5))
+    assert rel_fro(ops.pinv_R(_dev(Rr)).cpu().numpy(), np.linalg.pinv(Rr)) < 1e-12
+
+
 def test_residual_norm(rb):
     from rla4mor_b200 import reductor_ops as ops
     rs = np.random.RandomState(0)

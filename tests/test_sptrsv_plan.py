@@ -1,0 +1,78 @@
+"""Host logic of the sparse triangular solves (rla4mor_b200/factorization.py, csrc/sptrsv.cu):
+the C++ plan builder (levels, level-sorted order, groups of the narrow tail, re-packed CSR) is
+checked on the CPU by replaying the device schedule step by step in NumPy against SciPy.
+No GPU involved."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.sparse.linalg import splu, spsolve_triangular
+
+from rla4mor_b200.factorization import plan_triangular
+
+
+def _fem(nx):
+    ex = np.ones(nx)
+    T = sp.diags([-ex[:-1], 2 * ex, -ex[:-1]], [-1, 0, 1])
+    return (sp.kron(sp.eye(nx), T) + sp.kron(T, sp.eye(nx)) + 0.1 * sp.eye(nx * nx)).tocsc()
+
+
+def _replay(p, B, unit):
+    """What trsv_wide_kernel / trsv_group_kernel compute, in the same order."""
+    X = B.copy()
+    rowptr, col, val, order, split = p["rowptr"], p["col"], p["val"], p["order"], p["split"]
+    for lo, hi, kind in zip(p["step_lo"], p["step_hi"], p["step_kind"]):
+        rows = order[lo:hi]
+        if kind == 0:
+            new = {}
+            for i in rows:
+                e0, e1 = rowptr[i], rowptr[i + 1]
+                assert split[i] == e1
+                assert np.all(p["pos"][col[e0:e1]] < lo)              # only earlier steps
+                new[i] = (X[i] - val[e0:e1] @ X[col[e0:e1]]) / (1.0 if unit else p["diag"][i])
+            for i, v in new.items():
+                X[i] = v
+        else:
+            assert hi - lo <= 32
+            ext = []
+            for i in rows:                                             # phase 1: external sums, all rows at once
+                e0, e1 = rowptr[i], split[i]
+                assert np.all(p["pos"][col[e0:e1]] < lo)
+                ext.append(-(val[e0:e1] @ X[col[e0:e1]]))
+            xs = np.zeros((hi - lo,) + X.shape[1:])
+            for q, i in enumerate(rows):                               # phase 2: sequential inside the group
+                e0, e1 = split[i], rowptr[i + 1]
+                assert np.all(col[e0:e1] < q)                          # slots of earlier rows of the group
+                acc = X[i] + ext[q] - val[e0:e1] @ xs[col[e0:e1]]
+                xs[q] = acc / (1.0 if unit else p["diag"][i])
+                X[i] = xs[q]
+    return X
+
+
+@pytest.mark.parametrize("nx", [7, 40])
+def test_plan_replay_matches_scipy(nx):
+    A = _fem(nx)
+    n = A.shape[0]
+    lu = splu(A)
+    B = np.random.RandomState(0).standard_normal((n, 3))
+    for T, lower, unit in ((lu.L, True, True), (lu.U, False, False), (lu.U.T, True, False), (lu.L.T, False, True)):
+        p = plan_triangular(T.tocsr(), lower)
+        assert sorted(p["order"].tolist()) == list(range(n)) and np.all(p["pos"][p["order"]] == np.arange(n))
+        assert np.all(np.diff(p["level"][p["order"]]) >= 0)
+        assert p["step_lo"][0] == 0 and p["step_hi"][-1] == n and np.all(p["step_lo"][1:] == p["step_hi"][:-1])
+        ref = spsolve_triangular(T.tocsr(), B, lower=lower)
+        got = _replay(p, B, unit)
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-12
+
+
+def test_plan_small_cases():
+    # diagonal matrix: one level; strictly sequential chain: one group after another
+    p = plan_triangular(sp.eye(5, format="csr") * 2.0, True)
+    assert p["nlevels"] == 1 and p["nnz"] == 0 and np.allclose(p["diag"], 2.0)
+    n = 70
+    T = (sp.eye(n) + sp.diags([np.ones(n - 1)], [-1])).tocsr()
+    p = plan_triangular(T, True)
+    assert p["nlevels"] == n and p["nsteps"] == 3 and list(p["step_kind"]) == [1, 1, 1]
+    B = np.arange(n, dtype=float).reshape(-1, 1)
+    assert np.allclose(_replay(p, B, True), spsolve_triangular(T, B, lower=True))
+    with pytest.raises(Exception):
+        plan_triangular(sp.csr_matrix(np.array([[1.0, 2.0], [0.0, 1.0]])), True)       # entry above the diagonal
