@@ -231,36 +231,42 @@ int rla_residual_norm_f64(const double *S_dev, int64_t Q, int64_t k, int64_t r,
  * (mor/sketched_reductor.py:69,73).  The factorisation Pr A Pc = L U is SciPy SuperLU's, on the
  * host, as in the reference; L and U are uploaded as CSR.
  * rla_sptrsv_plan_host (HOST arrays in and out, plain C++ on the CPU, once per factor): level of
- * every row (lower != 0: dependencies j < i; else j > i), rows sorted by level (order_out, inverse
- * pos_out), the strictly triangular part re-packed as CSR with the entries of a row sorted by the
- * position of their column (rowptr2 n + 1, col2 / val2 up to nnz), the diagonal (1.0 where absent)
- * and the step list: step s covers order positions [step_lo[s], step_hi[s]); kind 0 = one level
- * of more than `narrow` independent rows, kind 1 = a group of at most group_rows (<= 32) rows cut
- * from a run of narrow levels; split_out[i] = first entry of row i that refers to a row of its
- * own group (for those entries col2 holds the slot inside the group).  step arrays: n entries.
+ * every row (lower != 0: dependencies j < i; else j > i), the processing order of the rows
+ * (order_out, inverse pos_out), the strictly triangular part re-packed as CSR with the entries of
+ * a row sorted by the position of their column (rowptr2 n + 1, col2 / val2 up to nnz), the
+ * diagonal (1.0 where absent), the GROUPS (group g = order positions [grp_start[g], grp_start[g] +
+ * grp_rows[g]), at most group_rows <= 32 rows that may depend on each other) and the STEPS:
+ * kind 0 = one level of more than wide_min rows, order positions [step_lo, step_hi), rows
+ * independent; kind 1 = groups [step_lo, step_hi), independent of each other (a band of
+ * consecutive levels split into its connected components), multi-row groups first and single-row
+ * groups from step_mid on, at most max_multi multi-row groups per step.  split_out[i] = first
+ * entry of row i that refers to a row of its own group; for those entries col2 holds the slot
+ * inside the group.  All output arrays hold n entries (rowptr2 n + 1, col2 / val2 nnz).
  * rla_sptrsv_transpose_in/out: (m, n) block of the reference layout <-> X (n, ldx) with the m
  * right-hand sides contiguous (ldx even, >= m), with the row / column permutation of the
  * factorisation applied on the way (perm_dev may be NULL): X[perm[i], c] = B[c, i] and
  * out[c, i] = X[perm[i], c].
- * rla_sptrsv_solve_f64: in-place T X = X, one launch per step (the step arrays stay on the
- * HOST); diag_dev NULL = unit diagonal; scratch_dev: rla_sptrsv_scratch_bytes(ldx) bytes,
- * zero-filled once by the caller. */
+ * rla_sptrsv_solve_f64: in-place T X = X, one or two launches per step (the step arrays stay on
+ * the HOST); diag_dev NULL = unit diagonal; scratch_dev: rla_sptrsv_scratch_bytes(ldx, max_multi)
+ * bytes, zero-filled once by the caller. */
 int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val,
-                         int lower, int narrow, int group_rows,
+                         int lower, int wide_min, int group_rows, int max_multi,
                          int32_t *level_out, int32_t *order_out, int32_t *pos_out,
                          int64_t *rowptr2, int32_t *col2, double *val2, double *diag_out,
-                         int64_t *split_out, int64_t *step_lo, int64_t *step_hi, int32_t *step_kind,
+                         int64_t *split_out, int64_t *grp_start, int32_t *grp_rows, int64_t *ngroups_out,
+                         int64_t *step_lo, int64_t *step_mid, int64_t *step_hi, int32_t *step_kind,
                          int64_t *nsteps_out, int32_t *nlevels_out);
 int rla_sptrsv_transpose_in_f64(const double *b_dev, int64_t m, int64_t n, int64_t ldb,
                                 const int32_t *perm_dev, double *x_dev, int64_t ldx, void *stream);
 int rla_sptrsv_transpose_out_f64(const double *x_dev, int64_t m, int64_t n, int64_t ldx,
                                  const int32_t *perm_dev, double *out_dev, int64_t ldo, void *stream);
-size_t rla_sptrsv_scratch_bytes(int64_t ldx);
+size_t rla_sptrsv_scratch_bytes(int64_t ldx, int max_multi);
 int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *col_dev, const double *val_dev,
                          const double *diag_dev, const int32_t *order_dev, const int32_t *pos_dev,
-                         const int64_t *split_dev,
-                         const int64_t *step_lo_host, const int64_t *step_hi_host, const int32_t *step_kind_host,
-                         int64_t nsteps, double *x_dev, int64_t m, int64_t ldx,
+                         const int64_t *split_dev, const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
+                         const int64_t *step_lo_host, const int64_t *step_mid_host, const int64_t *step_hi_host,
+                         const int32_t *step_kind_host, int64_t nsteps, int max_multi,
+                         double *x_dev, int64_t m, int64_t ldx,
                          void *scratch_dev, size_t scratch_bytes, void *stream);
 
 /* ------------------------------------------- row-sharded exchange (K5) -----

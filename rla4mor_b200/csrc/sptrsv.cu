@@ -79,137 +79,214 @@ struct TrsvArgs {
 
 constexpr int TRSV_GROUP = 32;                        // rows per group of the narrow tail
 
-// one level: warp = one row x one chunk of 64 right-hand sides
+constexpr int TRSV_WARPS = 16;                        // warps of a CTA that owns one row
+
+// -sum_e val[e] * X[col[e], c..c+1] over the entries [e0, e1) of one row, for warp `w` of `nw`
+// warps sharing the row.  A warp takes 32 consecutive entries at a time: (col, val) come in with
+// ONE coalesced load per lane and are broadcast by shuffles; the X rows are fetched 8 at a time
+// (8 independent 16-byte loads in flight per lane).  Every lane of the warp must call this.
+__device__ __forceinline__ double2 row_sum_warp(const TrsvArgs &a, int64_t e0, int64_t e1, int64_t c, bool live,
+                                                int w, int nw) {
+    const int lane = threadIdx.x & 31;
+    double2 acc = make_double2(0.0, 0.0);
+    for (int64_t base = e0 + 32 * (int64_t)w; base < e1; base += 32 * (int64_t)nw) {
+        const int64_t e = base + lane;
+        int32_t jc = 0;
+        double vc = 0.0;
+        if (e < e1) { jc = a.col[e]; vc = a.val[e]; }
+        const int cnt = (int)min((int64_t)32, e1 - base);
+        for (int t0 = 0; t0 < cnt; t0 += 8) {
+            int32_t j[8];
+            double v[8];
+            double2 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                j[u] = __shfl_sync(0xffffffffu, jc, (t0 + u) & 31);
+                v[u] = __shfl_sync(0xffffffffu, vc, (t0 + u) & 31);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                x[u] = (live && t0 + u < cnt) ? ldcg2(a.X + (int64_t)j[u] * a.ldx + c) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (t0 + u < cnt) { acc.x = fma(-v[u], x[u].x, acc.x); acc.y = fma(-v[u], x[u].y, acc.y); }
+            }
+        }
+    }
+    return acc;
+}
+
+// one wide level: warp = one row x one chunk of 64 right-hand sides
 __global__ void __launch_bounds__(256)
 trsv_wide_kernel(const TrsvArgs a, int64_t lo, int64_t hi) {
     const int lane = threadIdx.x & 31;
     const int64_t idx = lo + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (idx >= hi) return;
+    if (idx >= hi) return;                             // whole warp
     const int64_t c = (int64_t)blockIdx.y * TRSV_RHS + 2 * lane;
-    if (c >= a.ldx) return;
+    const bool live = c < a.ldx;
     const int64_t i = a.order[idx];
-    double *xi = a.X + i * a.ldx + c;
-    double2 acc = *reinterpret_cast<const double2 *>(xi);
-    const int64_t e1 = a.rowptr[i + 1];
-    int64_t e = a.rowptr[i];
-    for (; e + 4 <= e1; e += 4) {                      // four independent 16-byte loads in flight
-        int32_t j[4];
-        double v[4];
-        double2 x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { j[u] = a.col[e + u]; v[u] = a.val[e + u]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = ldcg2(a.X + (int64_t)j[u] * a.ldx + c);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { acc.x = fma(-v[u], x[u].x, acc.x); acc.y = fma(-v[u], x[u].y, acc.y); }
+    double2 acc = row_sum_warp(a, a.rowptr[i], a.rowptr[i + 1], c, live, 0, 1);
+    if (live) {
+        double *xi = a.X + i * a.ldx + c;
+        const double2 b = *reinterpret_cast<const double2 *>(xi);
+        acc.x += b.x; acc.y += b.y;
+        if (a.diag) { const double d = a.diag[i]; acc.x /= d; acc.y /= d; }
+        *reinterpret_cast<double2 *>(xi) = acc;
     }
-    for (; e < e1; ++e) {
-        const double v = a.val[e];
-        const double2 x = ldcg2(a.X + (int64_t)a.col[e] * a.ldx + c);
-        acc.x = fma(-v, x.x, acc.x); acc.y = fma(-v, x.y, acc.y);
-    }
-    if (a.diag) { const double d = a.diag[i]; acc.x /= d; acc.y /= d; }
-    *reinterpret_cast<double2 *>(xi) = acc;
 }
 
-// A GROUP of up to 32 consecutive rows of the narrow tail (several levels).  CTA r sums the
-// EXTERNAL entries of row r (columns solved by earlier launches) with its 8 warps; the last CTA
-// to arrive then resolves the group's internal triangular dependencies sequentially from shared
-// memory (one warp, lanes = right-hand sides).  One launch per group instead of one
-// synchronisation per level, and no spin-wait anywhere.
-__global__ void __launch_bounds__(256)
-trsv_group_kernel(const TrsvArgs a, int64_t g0, int nrows) {
-    __shared__ double2 part[8][32];
+// the same sum with the row split over the TRSV_WARPS warps of the CTA, combined in warp order;
+// result valid in warp 0
+__device__ __forceinline__ double2 row_sum_cta(const TrsvArgs &a, int64_t e0, int64_t e1, int64_t c, bool live,
+                                               double2 (*part)[32]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2 acc = row_sum_warp(a, e0, e1, c, live, warp, TRSV_WARPS);
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = part[0][lane];
+#pragma unroll
+        for (int w = 1; w < TRSV_WARPS; ++w) { acc.x += part[w][lane].x; acc.y += part[w][lane].y; }
+    }
+    return acc;
+}
+
+// One STEP of the schedule: a set of independent GROUPS.  A group is up to 32 rows that depend on
+// each other (a chain of consecutive levels inside one supernode of the factor) and, outside the
+// group, only on rows solved by earlier launches.  blockIdx.z = group, blockIdx.x = row of the
+// group, blockIdx.y = chunk of right-hand sides.  CTA (r, chunk, g) sums the EXTERNAL entries of
+// its row with all its warps; a single-row group is finished right there; otherwise the last CTA
+// of the group to arrive (ticket counter, no spin-wait) stages the group's internal entries and
+// right-hand sides in shared memory and resolves the internal dependencies sequentially (one
+// warp, lanes = right-hand sides).  One launch per ~32 levels instead of one per level.
+constexpr int TRSV_INT_MAX = TRSV_GROUP * (TRSV_GROUP - 1) / 2;
+__global__ void __launch_bounds__(32 * TRSV_WARPS)
+trsv_groups_kernel(const TrsvArgs a, const int64_t *__restrict__ grp_start, const int32_t *__restrict__ grp_rows,
+                   int64_t g_first) {
+    __shared__ double2 part[TRSV_WARPS][32];
     __shared__ double2 xs[TRSV_GROUP][32];
+    __shared__ double2 rhs[TRSV_GROUP][32];
+    __shared__ int s_start[TRSV_GROUP + 1];
+    __shared__ double s_diag[TRSV_GROUP];
+    __shared__ int s_icol[TRSV_INT_MAX];
+    __shared__ double s_ival[TRSV_INT_MAX];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gid = g_first + blockIdx.z;
+    const int nrows = grp_rows[gid];
     const int r = blockIdx.x;
+    if (r >= nrows) return;
+    const int64_t g0 = grp_start[gid];
     const int64_t c = (int64_t)blockIdx.y * TRSV_RHS + 2 * lane;
     const bool live = c < a.ldx;
     const int64_t i = a.order[g0 + r];
-    {
-        double2 acc = make_double2(0.0, 0.0);
-        if (live) {
-            const int64_t e1 = a.split[i];
-            int64_t e = a.rowptr[i] + warp;
-            for (; e + 24 < e1; e += 32) {             // four independent 16-byte loads in flight per lane
-                int32_t j[4];
-                double v[4];
-                double2 x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { j[u] = a.col[e + 8 * u]; v[u] = a.val[e + 8 * u]; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = ldcg2(a.X + (int64_t)j[u] * a.ldx + c);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { acc.x = fma(-v[u], x[u].x, acc.x); acc.y = fma(-v[u], x[u].y, acc.y); }
-            }
-            for (; e < e1; e += 8) {
-                const double v = a.val[e];
-                const double2 x = ldcg2(a.X + (int64_t)a.col[e] * a.ldx + c);
-                acc.x = fma(-v, x.x, acc.x); acc.y = fma(-v, x.y, acc.y);
-            }
-        }
-        part[warp][lane] = acc;
-        __syncthreads();
+    double2 acc = row_sum_cta(a, a.rowptr[i], a.split[i], c, live, part);
+    if (nrows == 1) {                                  // nothing internal: finish the row here
         if (warp == 0 && live) {
-            acc = part[0][lane];
-#pragma unroll
-            for (int w = 1; w < 8; ++w) { acc.x += part[w][lane].x; acc.y += part[w][lane].y; }
-            *reinterpret_cast<double2 *>(a.E + (int64_t)r * a.ldx + c) = acc;
+            double *xi = a.X + i * a.ldx + c;
+            const double2 b = *reinterpret_cast<const double2 *>(xi);
+            acc.x += b.x; acc.y += b.y;
+            if (a.diag) { const double d = a.diag[i]; acc.x /= d; acc.y /= d; }
+            *reinterpret_cast<double2 *>(xi) = acc;
         }
+        return;
     }
+    // groups of a step that have internal work are numbered 0.. in launch order: blockIdx.z
+    double *E = a.E + (int64_t)blockIdx.z * TRSV_GROUP * a.ldx;
+    unsigned int *counter = a.counter + (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+    if (warp == 0 && live) *reinterpret_cast<double2 *>(E + (int64_t)r * a.ldx + c) = acc;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicAdd(a.counter + blockIdx.y, 1u);
+        const unsigned int ticket = atomicAdd(counter, 1u);
         s_last = ticket == (unsigned int)nrows - 1;
-        if (s_last) a.counter[blockIdx.y] = 0;         // ready for the next group (next launch)
+        if (s_last) *counter = 0;                      // ready for the next launch
     }
     __syncthreads();
-    if (!s_last || warp != 0 || !live) return;
+    if (!s_last) return;
     __threadfence();
-    for (int q = 0; q < nrows; ++q) {
-        const int64_t iq = a.order[g0 + q];
-        double *xi = a.X + iq * a.ldx + c;
-        double2 acc = ldcg2(xi);
-        const double2 ext = ldcg2(a.E + (int64_t)q * a.ldx + c);
-        acc.x += ext.x; acc.y += ext.y;
-        const int64_t e1 = a.rowptr[iq + 1];
-        for (int64_t e = a.split[iq]; e < e1; ++e) {
-            const double v = a.val[e];
-            const double2 x = xs[a.col[e]][lane];        // internal entries store the slot in the group
-            acc.x = fma(-v, x.x, acc.x); acc.y = fma(-v, x.y, acc.y);
+    // stage: internal entries (slot, value) of every row, and b + external sum of every row
+    if (warp == 0) {                                   // offsets of the rows' internal entries: warp scan
+        int cnt = 0;
+        if (lane < nrows) {
+            const int64_t iq = a.order[g0 + lane];
+            cnt = (int)(a.rowptr[iq + 1] - a.split[iq]);
+            s_diag[lane] = a.diag ? a.diag[iq] : 1.0;
         }
-        if (a.diag) { const double d = a.diag[iq]; acc.x /= d; acc.y /= d; }
-        xs[q][lane] = acc;
-        *reinterpret_cast<double2 *>(xi) = acc;
-        __syncwarp();
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 0) s_start[0] = 0;
+        if (lane < nrows) s_start[lane + 1] = incl;
     }
+    __syncthreads();
+    for (int q = warp; q < nrows; q += TRSV_WARPS) {
+        const int64_t iq = a.order[g0 + q];
+        const int64_t e0 = a.split[iq];
+        const int cnt = s_start[q + 1] - s_start[q];
+        for (int t = lane; t < cnt; t += 32) {
+            s_icol[s_start[q] + t] = a.col[e0 + t];
+            s_ival[s_start[q] + t] = a.val[e0 + t];
+        }
+        if (live) {
+            const double2 b = ldcg2(a.X + iq * a.ldx + c), ext = ldcg2(E + (int64_t)q * a.ldx + c);
+            rhs[q][lane] = make_double2(b.x + ext.x, b.y + ext.y);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {                                   // whole warp (idle lanes compute on zeros, never stored)
+        for (int q = 0; q < nrows; ++q) {
+            double2 sum = live ? rhs[q][lane] : make_double2(0.0, 0.0);
+            for (int t = s_start[q]; t < s_start[q + 1]; ++t) {
+                const double v = s_ival[t];
+                const double2 x = xs[s_icol[t]][lane];
+                sum.x = fma(-v, x.x, sum.x); sum.y = fma(-v, x.y, sum.y);
+            }
+            if (a.diag) { const double d = s_diag[q]; sum.x /= d; sum.y /= d; }
+            xs[q][lane] = sum;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (live)
+        for (int q = warp; q < nrows; q += TRSV_WARPS)
+            *reinterpret_cast<double2 *>(a.X + (int64_t)a.order[g0 + q] * a.ldx + c) = xs[q][lane];
 }
 
 }  // namespace rla
 
 using namespace rla;
 
-// Host-side analysis of one triangular CSR factor (HOST arrays in, HOST arrays out):
+// Host-side analysis of one triangular CSR factor (HOST arrays in, HOST arrays out; plain C++):
 //   level_out[i]   longest dependency chain ending in row i (lower != 0: deps j < i, else j > i)
-//   order_out      rows sorted by level (stable), pos_out its inverse
+//   order_out      the processing order of the rows, pos_out its inverse
 //   rowptr2/col2/val2  the strictly triangular part, entries of each row sorted by pos[col]
 //   diag_out       the diagonal (1.0 where absent)
-//   steps: step s covers order positions [step_lo[s], step_hi[s]); step_kind 0 = one level of
-//   more than `narrow` rows (rows independent), 1 = a group of at most `group_rows` rows cut from a
-//   run of narrow levels (dependencies inside the group allowed); split_out[i] = first entry of
-//   row i whose column is inside its own group (row end for rows of wide levels).
-// Returns the number of steps through nsteps_out (arrays must hold n entries).
+//   groups         group g = order positions [grp_start[g], grp_start[g] + grp_rows[g]), <= group_rows rows
+//   steps          kind 0: ONE level of more than `wide_min` rows, order positions [step_lo, step_hi),
+//                  rows independent; kind 1: groups [step_lo, step_hi), independent of each other, the
+//                  multi-row groups first, then (from step_mid on) the single-row groups.
+//   split_out[i]   first entry of row i that refers to a row of its own group (row end when there is
+//                  none); for those entries col2 holds the slot of the column inside the group.
+// A kind-1 step is a BAND of up to `group_rows` consecutive levels whose connected components
+// (dependencies inside the band) all have at most `group_rows` rows: each component is a group.  The
+// band is shortened until that holds (a single level always qualifies: singleton groups).  At most
+// max_multi multi-row groups per step (they need scratch).  Arrays of n entries each.
 extern "C" int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val,
-                                    int lower, int narrow, int group_rows,
+                                    int lower, int wide_min, int group_rows, int max_multi,
                                     int32_t *level_out, int32_t *order_out, int32_t *pos_out,
                                     int64_t *rowptr2, int32_t *col2, double *val2, double *diag_out,
-                                    int64_t *split_out, int64_t *step_lo, int64_t *step_hi, int32_t *step_kind,
+                                    int64_t *split_out, int64_t *grp_start, int32_t *grp_rows, int64_t *ngroups_out,
+                                    int64_t *step_lo, int64_t *step_mid, int64_t *step_hi, int32_t *step_kind,
                                     int64_t *nsteps_out, int32_t *nlevels_out) {
     RLA_REQUIRE(n >= 0 && rowptr && level_out && order_out && pos_out && rowptr2 && diag_out && split_out &&
-                step_lo && step_hi && step_kind && nsteps_out && nlevels_out, "rla_sptrsv_plan_host: null pointer");
-    RLA_REQUIRE(narrow >= 1 && group_rows >= 1 && group_rows <= TRSV_GROUP, "rla_sptrsv_plan_host: bad group size");
+                grp_start && grp_rows && ngroups_out && step_lo && step_mid && step_hi && step_kind && nsteps_out &&
+                nlevels_out, "rla_sptrsv_plan_host: null pointer");
+    RLA_REQUIRE(wide_min >= 1 && group_rows >= 1 && group_rows <= TRSV_GROUP && max_multi >= 1,
+                "rla_sptrsv_plan_host: bad parameters");
     int32_t nl = 0;
     for (int64_t t = 0; t < n; ++t) {
         const int64_t i = lower ? t : n - 1 - t;
@@ -236,28 +313,95 @@ extern "C" int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int3
             pos_out[i] = (int32_t)p;
         }
     }
-    // steps
-    int64_t ns = 0;
-    std::vector<int64_t> group_start((size_t)n, 0);    // per order position: start of its group (wide: row itself irrelevant)
+    std::vector<int64_t> gstart_of_pos((size_t)n, -1);  // start position of the group of the row at a position
+    std::vector<int32_t> parent, csize, band_rows, comp_first;
+    int64_t ns = 0, ng = 0;
     int32_t l = 0;
     while (l < nl) {
         const int64_t rows = lvlptr[(size_t)l + 1] - lvlptr[l];
-        if (rows > narrow) {
-            step_lo[ns] = lvlptr[l]; step_hi[ns] = lvlptr[(size_t)l + 1]; step_kind[ns] = 0; ++ns;
-            for (int64_t p = lvlptr[l]; p < lvlptr[(size_t)l + 1]; ++p) group_start[p] = -1;
+        if (rows > wide_min) {
+            step_lo[ns] = lvlptr[l]; step_mid[ns] = lvlptr[(size_t)l + 1]; step_hi[ns] = lvlptr[(size_t)l + 1];
+            step_kind[ns] = 0; ++ns;
             ++l;
-        } else {
-            int32_t end = l + 1;
-            while (end < nl && lvlptr[(size_t)end + 1] - lvlptr[end] <= narrow) ++end;
-            for (int64_t p = lvlptr[l]; p < lvlptr[end]; p += group_rows) {
-                const int64_t q = std::min<int64_t>(p + group_rows, lvlptr[end]);
-                step_lo[ns] = p; step_hi[ns] = q; step_kind[ns] = 1; ++ns;
-                for (int64_t t = p; t < q; ++t) group_start[t] = p;
+            continue;
+        }
+        // longest band [l, l + W) of non-wide levels whose components have at most group_rows rows
+        int32_t W = 1;
+        while (W < group_rows && l + W < nl && lvlptr[(size_t)l + W + 1] - lvlptr[(size_t)l + W] <= wide_min) ++W;
+        const int64_t p0 = lvlptr[l];
+        for (;; W = std::max(1, W / 2)) {
+            const int64_t p1 = lvlptr[(size_t)l + W];
+            const int64_t nb = p1 - p0;
+            parent.resize((size_t)nb); csize.assign((size_t)nb, 1);
+            for (int64_t t = 0; t < nb; ++t) parent[t] = (int32_t)t;
+            bool ok = true;
+            if (W > 1) {
+                auto find = [&](int32_t x) {
+                    while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+                    return x;
+                };
+                for (int64_t p = p0; p < p1 && ok; ++p) {
+                    const int64_t i = order_out[p];
+                    for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+                        const int32_t j = col[e];
+                        if (j == i || pos_out[j] < p0) continue;      // outside the band (earlier levels)
+                        int32_t ra = find((int32_t)(p - p0)), rb = find((int32_t)(pos_out[j] - p0));
+                        if (ra == rb) continue;
+                        if (csize[ra] < csize[rb]) std::swap(ra, rb);
+                        parent[rb] = ra;
+                        csize[ra] += csize[rb];
+                        if (csize[ra] > group_rows) { ok = false; break; }
+                    }
+                }
+                if (ok) for (int64_t t = 0; t < nb; ++t) parent[t] = find((int32_t)t);
             }
-            l = end;
+            if (!ok) continue;                                         // shorten the band
+            // accepted: components -> groups; rows of a component stay in level order (stable)
+            band_rows.resize((size_t)nb);
+            for (int64_t t = 0; t < nb; ++t) band_rows[t] = order_out[p0 + t];
+            // multi-row components first (in order of first appearance), then singletons
+            comp_first.assign((size_t)nb, -1);
+            std::vector<std::vector<int32_t>> multi;
+            std::vector<int32_t> single;
+            for (int64_t t = 0; t < nb; ++t) {
+                const int32_t root = parent[t];
+                if (csize[root] == 1) { single.push_back((int32_t)t); continue; }
+                if (comp_first[root] < 0) { comp_first[root] = (int32_t)multi.size(); multi.emplace_back(); }
+                multi[comp_first[root]].push_back((int32_t)t);
+            }
+            int64_t p = p0;
+            size_t mi = 0, si = 0;
+            // emit steps: at most max_multi multi-row groups (and at most 65535 groups) per step
+            while (mi < multi.size() || si < single.size()) {
+                step_kind[ns] = 1;
+                step_lo[ns] = ng;
+                size_t took = 0;
+                for (; mi < multi.size() && took < (size_t)max_multi; ++mi, ++took) {
+                    grp_start[ng] = p; grp_rows[ng] = (int32_t)multi[mi].size();
+                    for (int32_t t : multi[mi]) {
+                        order_out[p] = band_rows[t]; pos_out[band_rows[t]] = (int32_t)p; gstart_of_pos[p] = grp_start[ng];
+                        ++p;
+                    }
+                    ++ng;
+                }
+                step_mid[ns] = ng;
+                if (mi == multi.size()) {
+                    for (took = 0; si < single.size() && took < 65535; ++si, ++took) {
+                        const int32_t t = single[si];
+                        grp_start[ng] = p; grp_rows[ng] = 1;
+                        order_out[p] = band_rows[t]; pos_out[band_rows[t]] = (int32_t)p; gstart_of_pos[p] = p;
+                        ++p; ++ng;
+                    }
+                }
+                step_hi[ns] = ng;
+                ++ns;
+            }
+            l += W;
+            break;
         }
     }
     *nsteps_out = ns;
+    *ngroups_out = ng;
     // strictly triangular CSR with entries sorted by the position of their column
     std::vector<std::pair<int32_t, int64_t>> tmp;
     int64_t w = 0;
@@ -270,7 +414,7 @@ extern "C" int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int3
             tmp.emplace_back(pos_out[col[e]], e);
         }
         std::sort(tmp.begin(), tmp.end());
-        const int64_t gs = group_start[pos_out[i]];
+        const int64_t gs = gstart_of_pos[pos_out[i]];
         int64_t sp = -1;
         for (const auto &pe : tmp) {
             if (sp < 0 && gs >= 0 && pe.first >= gs) sp = w;
@@ -312,44 +456,55 @@ extern "C" int rla_sptrsv_transpose_out_f64(const double *x_dev, int64_t m, int6
 
 // In-place triangular solve T X = X on the (n, ldx) block (right-hand sides contiguous), driven by
 // the step list of rla_sptrsv_plan_host (HOST arrays step_*); all other arrays on the device.
-// scratch_dev: rla_sptrsv_scratch_bytes(ldx) bytes, zero-filled once by the caller.
-extern "C" size_t rla_sptrsv_scratch_bytes(int64_t ldx) {
+// scratch_dev: rla_sptrsv_scratch_bytes(ldx, max_multi) bytes, zero-filled once by the caller.
+extern "C" size_t rla_sptrsv_scratch_bytes(int64_t ldx, int max_multi) {
     const size_t chunks = (size_t)((ldx + TRSV_RHS - 1) / TRSV_RHS);
-    return (size_t)TRSV_GROUP * (size_t)ldx * sizeof(double) + chunks * sizeof(unsigned int) + 64;
+    return (size_t)max_multi * ((size_t)TRSV_GROUP * (size_t)ldx * sizeof(double) + chunks * sizeof(unsigned int)) + 64;
 }
 
 extern "C" int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *col_dev, const double *val_dev,
                                     const double *diag_dev, const int32_t *order_dev, const int32_t *pos_dev,
-                                    const int64_t *split_dev,
-                                    const int64_t *step_lo, const int64_t *step_hi, const int32_t *step_kind,
-                                    int64_t nsteps, double *x_dev, int64_t m, int64_t ldx,
+                                    const int64_t *split_dev, const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
+                                    const int64_t *step_lo, const int64_t *step_mid, const int64_t *step_hi,
+                                    const int32_t *step_kind, int64_t nsteps, int max_multi,
+                                    double *x_dev, int64_t m, int64_t ldx,
                                     void *scratch_dev, size_t scratch_bytes, void *stream) {
-    RLA_REQUIRE(nsteps >= 0 && m >= 0 && ldx >= m && (ldx & 1) == 0, "rla_sptrsv_solve_f64: bad sizes");
+    RLA_REQUIRE(nsteps >= 0 && m >= 0 && ldx >= m && (ldx & 1) == 0 && max_multi >= 1, "rla_sptrsv_solve_f64: bad sizes");
     if (nsteps == 0 || m == 0) return RLA_OK;
-    RLA_REQUIRE(rowptr_dev && col_dev && val_dev && order_dev && pos_dev && split_dev && step_lo && step_hi &&
-                step_kind && x_dev && scratch_dev, "rla_sptrsv_solve_f64: null pointer");
+    RLA_REQUIRE(rowptr_dev && col_dev && val_dev && order_dev && pos_dev && split_dev && grp_start_dev && grp_rows_dev &&
+                step_lo && step_mid && step_hi && step_kind && x_dev && scratch_dev, "rla_sptrsv_solve_f64: null pointer");
     RLA_REQUIRE(((uintptr_t)x_dev & 15) == 0 && ((uintptr_t)scratch_dev & 15) == 0,
                 "rla_sptrsv_solve_f64: X and scratch must be 16-byte aligned");
-    if (scratch_bytes < rla_sptrsv_scratch_bytes(ldx))
+    if (scratch_bytes < rla_sptrsv_scratch_bytes(ldx, max_multi))
         return fail(RLA_ERR_WORKSPACE, "rla_sptrsv_solve_f64: scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     double *E = static_cast<double *>(scratch_dev);
-    unsigned int *counter = reinterpret_cast<unsigned int *>(E + (size_t)TRSV_GROUP * ldx);
+    unsigned int *counter = reinterpret_cast<unsigned int *>(E + (size_t)max_multi * TRSV_GROUP * ldx);
     TrsvArgs a = {rowptr_dev, col_dev, val_dev, diag_dev, order_dev, pos_dev, split_dev, x_dev, E, counter, ldx, m};
     const unsigned chunks = (unsigned)((ldx + TRSV_RHS - 1) / TRSV_RHS);
     RLA_REQUIRE(chunks <= 65535, "rla_sptrsv_solve_f64: too many right-hand sides");
     for (int64_t s = 0; s < nsteps; ++s) {
-        const int64_t rows = step_hi[s] - step_lo[s];
-        RLA_REQUIRE(rows >= 1, "rla_sptrsv_solve_f64: empty step %lld", (long long)s);
         if (step_kind[s] == 0) {
+            const int64_t rows = step_hi[s] - step_lo[s];
+            RLA_REQUIRE(rows >= 1, "rla_sptrsv_solve_f64: empty step %lld", (long long)s);
             dim3 grid((unsigned)((rows + 7) / 8), chunks);
             trsv_wide_kernel<<<grid, 256, 0, st>>>(a, step_lo[s], step_hi[s]);
-        } else {
-            RLA_REQUIRE(rows <= TRSV_GROUP, "rla_sptrsv_solve_f64: group of %lld rows", (long long)rows);
-            dim3 grid((unsigned)rows, chunks);
-            trsv_group_kernel<<<grid, 256, 0, st>>>(a, step_lo[s], (int)rows);
+            count_launch();
+            continue;
         }
-        count_launch();
+        const int64_t nmulti = step_mid[s] - step_lo[s], nsingle = step_hi[s] - step_mid[s];
+        RLA_REQUIRE(nmulti >= 0 && nsingle >= 0 && nmulti <= max_multi && nsingle <= 65535 && nmulti + nsingle >= 1,
+                    "rla_sptrsv_solve_f64: bad step %lld", (long long)s);
+        if (nmulti > 0) {
+            dim3 grid(TRSV_GROUP, chunks, (unsigned)nmulti);
+            trsv_groups_kernel<<<grid, 32 * TRSV_WARPS, 0, st>>>(a, grp_start_dev, grp_rows_dev, step_lo[s]);
+            count_launch();
+        }
+        if (nsingle > 0) {
+            dim3 grid(1, chunks, (unsigned)nsingle);
+            trsv_groups_kernel<<<grid, 32 * TRSV_WARPS, 0, st>>>(a, grp_start_dev, grp_rows_dev, step_mid[s]);
+            count_launch();
+        }
     }
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;

@@ -47,7 +47,7 @@ def operator_to_cholesky(operator=None, factor=None):
     return MatrixOperator(M, source_id, range_id)
 
 
-def plan_triangular(T, lower, narrow=32, group=32):
+def plan_triangular(T, lower, wide_min=4096, group=32, max_multi=256):
     """Host analysis of one triangular factor (C++ in librla_b200.so, no GPU involved): dict of
     NumPy arrays -- see rla_sptrsv_plan_host in include/rla_b200.h."""
     T = T.tocsr()
@@ -56,43 +56,50 @@ def plan_triangular(T, lower, narrow=32, group=32):
     col = np.ascontiguousarray(T.indices, dtype=np.int32)
     val = np.ascontiguousarray(T.data, dtype=np.float64)
     nnz = int(T.nnz)
-    level, order, pos = (np.empty(max(n, 1), dtype=np.int32) for _ in range(3))
+    n1 = max(n, 1)
+    level, order, pos = (np.empty(n1, dtype=np.int32) for _ in range(3))
     rowptr2 = np.empty(n + 1, dtype=np.int64)
     col2, val2 = np.empty(max(nnz, 1), dtype=np.int32), np.empty(max(nnz, 1), dtype=np.float64)
-    diag, split = np.empty(max(n, 1), dtype=np.float64), np.empty(max(n, 1), dtype=np.int64)
-    step_lo, step_hi = np.empty(max(n, 1), dtype=np.int64), np.empty(max(n, 1), dtype=np.int64)
-    step_kind = np.empty(max(n, 1), dtype=np.int32)
-    nsteps, nlev = ctypes.c_int64(0), ctypes.c_int32(0)
+    diag, split = np.empty(n1, dtype=np.float64), np.empty(n1, dtype=np.int64)
+    grp_start, grp_rows = np.empty(n1, dtype=np.int64), np.empty(n1, dtype=np.int32)
+    step_lo, step_mid, step_hi = (np.empty(n1, dtype=np.int64) for _ in range(3))
+    step_kind = np.empty(n1, dtype=np.int32)
+    nsteps, ngroups, nlev = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
     check(lib().rla_sptrsv_plan_host(n, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, 1 if lower else 0,
-                                     int(narrow), int(group), level.ctypes.data, order.ctypes.data, pos.ctypes.data,
+                                     int(wide_min), int(group), int(max_multi),
+                                     level.ctypes.data, order.ctypes.data, pos.ctypes.data,
                                      rowptr2.ctypes.data, col2.ctypes.data, val2.ctypes.data, diag.ctypes.data,
-                                     split.ctypes.data, step_lo.ctypes.data, step_hi.ctypes.data,
+                                     split.ctypes.data, grp_start.ctypes.data, grp_rows.ctypes.data, ctypes.byref(ngroups),
+                                     step_lo.ctypes.data, step_mid.ctypes.data, step_hi.ctypes.data,
                                      step_kind.ctypes.data, ctypes.byref(nsteps), ctypes.byref(nlev)),
           "rla_sptrsv_plan_host")
-    ns, nz = int(nsteps.value), int(rowptr2[n])
-    return dict(n=n, nlevels=int(nlev.value), nsteps=ns, level=level[:n], order=order[:n], pos=pos[:n],
+    ns, ng, nz = int(nsteps.value), int(ngroups.value), int(rowptr2[n])
+    c = np.ascontiguousarray
+    return dict(n=n, nlevels=int(nlev.value), nsteps=ns, ngroups=ng, max_multi=int(max_multi),
+                level=level[:n], order=order[:n], pos=pos[:n],
                 rowptr=rowptr2, col=col2[:max(nz, 1)], val=val2[:max(nz, 1)], nnz=nz, diag=diag[:n], split=split[:n],
-                step_lo=np.ascontiguousarray(step_lo[:ns]), step_hi=np.ascontiguousarray(step_hi[:ns]),
-                step_kind=np.ascontiguousarray(step_kind[:ns]))
+                grp_start=c(grp_start[:max(ng, 1)]), grp_rows=c(grp_rows[:max(ng, 1)]),
+                step_lo=c(step_lo[:ns]), step_mid=c(step_mid[:ns]), step_hi=c(step_hi[:ns]), step_kind=c(step_kind[:ns]))
 
 
 class TriangularFactor:
-    """One triangular CSR matrix on the device with its schedule (levels, rows sorted by level,
-    groups of the narrow tail: plan_triangular)."""
-
-    NARROW = 32          # levels of at most this many rows are cut into groups
-    GROUP = 32
+    """One triangular CSR matrix on the device with its schedule (levels, bands of levels split
+    into independent groups: plan_triangular)."""
 
     def __init__(self, T, lower, unit_diagonal, device):
         torch = require_cuda()
-        p = plan_triangular(T, lower, self.NARROW, self.GROUP)
+        p = plan_triangular(T, lower)
         self.n, self.lower = p["n"], bool(lower)
-        self.nlevels, self.nsteps, self.nnz = p["nlevels"], p["nsteps"], p["nnz"]
-        self.step_lo, self.step_hi, self.step_kind = p["step_lo"], p["step_hi"], p["step_kind"]
+        self.nlevels, self.nsteps, self.nnz, self.ngroups = p["nlevels"], p["nsteps"], p["nnz"], p["ngroups"]
+        self.max_multi = p["max_multi"]
+        self.step_lo, self.step_mid, self.step_hi, self.step_kind = p["step_lo"], p["step_mid"], p["step_hi"], p["step_kind"]
+        self.launches = int((self.step_kind == 0).sum() + ((self.step_kind == 1) & (self.step_mid > self.step_lo)).sum()
+                            + ((self.step_kind == 1) & (self.step_hi > self.step_mid)).sum())
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
         self.rowptr, self.col, self.val = dev(p["rowptr"]), dev(p["col"]), dev(p["val"])
         self.diag = None if unit_diagonal else dev(p["diag"])
         self.order, self.pos, self.split = dev(p["order"]), dev(p["pos"]), dev(p["split"])
+        self.grp_start, self.grp_rows = dev(p["grp_start"]), dev(p["grp_rows"])
         self._scratch = {}
 
     def solve_inplace(self, X, m):
@@ -101,14 +108,16 @@ class TriangularFactor:
         ldx = X.stride(0)
         key = (ldx, X.device.index)
         if key not in self._scratch:
-            self._scratch[key] = torch.zeros(lib().rla_sptrsv_scratch_bytes(ldx), dtype=torch.uint8, device=X.device)
+            self._scratch[key] = torch.zeros(lib().rla_sptrsv_scratch_bytes(ldx, self.max_multi), dtype=torch.uint8,
+                                             device=X.device)
         sc = self._scratch[key]
         check(lib().rla_sptrsv_solve_f64(self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
                                          None if self.diag is None else self.diag.data_ptr(), self.order.data_ptr(),
-                                         self.pos.data_ptr(), self.split.data_ptr(), self.step_lo.ctypes.data,
+                                         self.pos.data_ptr(), self.split.data_ptr(), self.grp_start.data_ptr(),
+                                         self.grp_rows.data_ptr(), self.step_lo.ctypes.data, self.step_mid.ctypes.data,
                                          self.step_hi.ctypes.data, self.step_kind.ctypes.data, self.nsteps,
-                                         X.data_ptr(), int(m), ldx, sc.data_ptr(), sc.numel(), stream_ptr()),
-              "rla_sptrsv_solve_f64")
+                                         self.max_multi, X.data_ptr(), int(m), ldx, sc.data_ptr(), sc.numel(),
+                                         stream_ptr()), "rla_sptrsv_solve_f64")
         return X
 
 

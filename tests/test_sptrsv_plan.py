@@ -17,34 +17,35 @@ def _fem(nx):
 
 
 def _replay(p, B, unit):
-    """What trsv_wide_kernel / trsv_group_kernel compute, in the same order."""
+    """What trsv_wide_kernel / trsv_groups_kernel compute, step by step."""
     X = B.copy()
-    rowptr, col, val, order, split = p["rowptr"], p["col"], p["val"], p["order"], p["split"]
-    for lo, hi, kind in zip(p["step_lo"], p["step_hi"], p["step_kind"]):
-        rows = order[lo:hi]
+    rowptr, col, val, order, split, pos = p["rowptr"], p["col"], p["val"], p["order"], p["split"], p["pos"]
+    done = np.zeros(p["n"], dtype=bool)
+    for lo, mid, hi, kind in zip(p["step_lo"], p["step_mid"], p["step_hi"], p["step_kind"]):
+        new = {}
         if kind == 0:
-            new = {}
-            for i in rows:
+            for i in order[lo:hi]:
                 e0, e1 = rowptr[i], rowptr[i + 1]
-                assert split[i] == e1
-                assert np.all(p["pos"][col[e0:e1]] < lo)              # only earlier steps
+                assert split[i] == e1 and np.all(done[col[e0:e1]])        # only rows of earlier steps
                 new[i] = (X[i] - val[e0:e1] @ X[col[e0:e1]]) / (1.0 if unit else p["diag"][i])
-            for i, v in new.items():
-                X[i] = v
         else:
-            assert hi - lo <= 32
-            ext = []
-            for i in rows:                                             # phase 1: external sums, all rows at once
-                e0, e1 = rowptr[i], split[i]
-                assert np.all(p["pos"][col[e0:e1]] < lo)
-                ext.append(-(val[e0:e1] @ X[col[e0:e1]]))
-            xs = np.zeros((hi - lo,) + X.shape[1:])
-            for q, i in enumerate(rows):                               # phase 2: sequential inside the group
-                e0, e1 = split[i], rowptr[i + 1]
-                assert np.all(col[e0:e1] < q)                          # slots of earlier rows of the group
-                acc = X[i] + ext[q] - val[e0:e1] @ xs[col[e0:e1]]
-                xs[q] = acc / (1.0 if unit else p["diag"][i])
-                X[i] = xs[q]
+            assert hi - lo >= 1 and mid - lo <= p["max_multi"]
+            for g in range(lo, hi):
+                g0, nr = p["grp_start"][g], p["grp_rows"][g]
+                assert 1 <= nr <= 32 and (nr > 1) == (g < mid)
+                rows = order[g0:g0 + nr]
+                xs = np.zeros((nr,) + X.shape[1:])
+                for q, i in enumerate(rows):
+                    e0, sp, e1 = rowptr[i], split[i], rowptr[i + 1]
+                    assert np.all(done[col[e0:sp]])                       # external: earlier steps only
+                    assert np.all(col[sp:e1] < q)                         # internal: earlier slots of the group
+                    acc = X[i] - val[e0:sp] @ X[col[e0:sp]] - val[sp:e1] @ xs[col[sp:e1]]
+                    xs[q] = acc / (1.0 if unit else p["diag"][i])
+                    new[i] = xs[q]
+        for i, v in new.items():                                          # a step only becomes visible at its end
+            X[i] = v
+            done[i] = True
+    assert done.all()
     return X
 
 
@@ -57,8 +58,6 @@ def test_plan_replay_matches_scipy(nx):
     for T, lower, unit in ((lu.L, True, True), (lu.U, False, False), (lu.U.T, True, False), (lu.L.T, False, True)):
         p = plan_triangular(T.tocsr(), lower)
         assert sorted(p["order"].tolist()) == list(range(n)) and np.all(p["pos"][p["order"]] == np.arange(n))
-        assert np.all(np.diff(p["level"][p["order"]]) >= 0)
-        assert p["step_lo"][0] == 0 and p["step_hi"][-1] == n and np.all(p["step_lo"][1:] == p["step_hi"][:-1])
         ref = spsolve_triangular(T.tocsr(), B, lower=lower)
         got = _replay(p, B, unit)
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-12
@@ -72,6 +71,7 @@ def test_plan_small_cases():
     T = (sp.eye(n) + sp.diags([np.ones(n - 1)], [-1])).tocsr()
     p = plan_triangular(T, True)
     assert p["nlevels"] == n and p["nsteps"] == 3 and list(p["step_kind"]) == [1, 1, 1]
+    assert list(p["grp_rows"][:p["ngroups"]]) == [32, 32, 6]
     B = np.arange(n, dtype=float).reshape(-1, 1)
     assert np.allclose(_replay(p, B, True), spsolve_triangular(T, B, lower=True))
     with pytest.raises(Exception):

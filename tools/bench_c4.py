@@ -1,0 +1,92 @@
+"""BASELINE.json configs[3]: SketchedReductor on a thermal-block-like FEM problem, n = 1e6, Q = 4
+affine terms, WITH the inverse product R^-1 in front of every sketch (Theta R^-1 A_q U):
+CSR SpMM, sparse-LU solve (two sparse triangular solves on the device), sketch, and the whole
+extend_basis; the CPU reference (SciPy SuperLU solve, what the reference's InverseLuOperator
+calls) timed beside it on a subset of the right-hand sides.
+
+    python tools/bench_c4.py [nx] [m]        # default 1000 64
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rla4mor_b200 as rb
+from rla4mor_b200.factorization import InverseLuOperator
+
+
+def timeit(f, iters=3):
+    f(); torch.cuda.synchronize(); ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); f(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return min(ts)
+
+
+def fem_terms(nx, Q=4):
+    n = nx * nx
+    ex = np.ones(nx)
+    T = sp.diags([-ex[:-1], 2 * ex, -ex[:-1]], [-1, 0, 1])
+    L = (sp.kron(sp.eye(nx), T) + sp.kron(T, sp.eye(nx))).tocsr()
+    idx = np.arange(n); blk = (idx // nx >= nx // 2) * 2 + (idx % nx >= nx // 2)
+    terms = [(sp.diags((blk == q % 4).astype(float) + 0.01) @ L @ sp.diags((blk == q % 4).astype(float) + 0.01)
+              + 1e-3 * sp.eye(n)).tocsr() for q in range(Q)]
+    return terms, (L + sp.eye(n)).tocsc(), n
+
+
+def main():
+    nx = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    m = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    k = 1000
+    terms, R, n = fem_terms(nx)
+    res = {"workload": "sketched_reductor_c4", "n": n, "Q": len(terms), "m": m, "k": k}
+    space = rb.DeviceVectorSpace(n, id="S")
+    ops_dev = [rb.MatrixOperator(A, source_id="S", range_id="S") for A in terms]
+    t0 = time.time()
+    rinv = InverseLuOperator(rb.MatrixOperator(R, source_id="S", range_id="S"), symetric=True)
+    res["host_splu_s"] = time.time() - t0
+    lu = rinv._device_lu
+    t0 = time.time(); fL, fU = lu._factors(False); res["host_plan_s"] = time.time() - t0
+    res["L"] = {"nnz": fL.nnz, "levels": fL.nlevels, "launches": fL.nsteps, "groups": int((fL.step_kind == 1).sum())}
+    res["U"] = {"nnz": fU.nnz, "levels": fU.nlevels, "launches": fU.nsteps, "groups": int((fU.step_kind == 1).sum())}
+    U = torch.randn(m, n, dtype=torch.float64, device="cuda")
+    Uva = space.from_numpy(U)
+    res["spmm_ms"] = timeit(lambda: ops_dev[0].apply(Uva))
+    V1 = ops_dev[0].apply(Uva)
+    res["lu_solve_ms"] = timeit(lambda: rinv.apply(V1))
+    ldx = m + (m & 1)
+    X = torch.randn(n, ldx, dtype=torch.float64, device="cuda")
+    res["L_solve_ms"] = timeit(lambda: fL.solve_inplace(X.clone(), m))
+    res["U_solve_ms"] = timeit(lambda: fU.solve_inplace(X.clone(), m))
+    res["clone_ms"] = timeit(lambda: X.clone())
+    # algorithmic traffic of one solve: every off-diagonal entry reads 8*m bytes of X and 12 bytes of the factor
+    byts = (fL.nnz + fU.nnz) * (8 * m + 12) + 4 * n * m * 8
+    res["lu_solve_algorithmic_GBs"] = byts / res["lu_solve_ms"] / 1e6
+    # parity against SuperLU on a few right-hand sides, and the CPU time of the reference's call
+    sub = min(m, 8)
+    Vh = V1.data[:sub].cpu().numpy()
+    t0 = time.time(); ref = rinv.factorization.solve(Vh.T).T; cpu_s = time.time() - t0
+    got = rinv.apply(space.from_numpy(V1.data[:sub])).to_numpy()
+    res["parity_rel_fro_vs_superlu"] = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    res["cpu_superlu_solve_s"] = {"rhs": sub, "seconds": cpu_s, "extrapolated_to_m_s": cpu_s * m / sub,
+                                  "host_cpus": os.cpu_count()}
+    for kind, opt in (("srht", {"range_dim": k}), ("gauss", {"range_dim": k, "rng": "philox"})):
+        emb = (rb.SrhtEmbedding if kind == "srht" else rb.GaussianEmbedding)(source=space, options=opt, _seed=0)
+        res[f"sketch_{kind}_ms"] = timeit(lambda: emb.apply(U))
+        for name, inv in (("identity_product", None), ("lu_inverse_product", rinv)):
+            def ext():
+                red = rb.SketchedReductor(ops_dev, [torch.ones(n, dtype=torch.float64, device="cuda")], emb,
+                                          inverse_product=inv)
+                red.extend_basis(U)
+                return red
+            res[f"extend_basis_{kind}_{name}_ms"] = timeit(ext, 2)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
