@@ -218,7 +218,8 @@ def run_ours(args):
         # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries only the JSON line
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     lib = rb.lib()
     peaks, peak_src = measured_peaks()
 

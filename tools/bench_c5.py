@@ -146,7 +146,8 @@ def main():
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"                        # keep NCCL's banner off stdout
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     peaks = {}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
