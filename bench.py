@@ -361,12 +361,16 @@ def run_ours(args):
         torch.cuda.empty_cache()
         return res
 
-    primary = run_workload(args.workload, not args.no_e2e, not args.no_cpu_baseline, args.steps, args.warmup)
-    host_block_np = primary.pop("_host_block", None)
     secondary = []
     if not args.no_secondary and args.workload == "gauss_c2":
+        # configs[2] first: the 137 GB block needs the whole HBM, and every workload is then timed
+        # from an idle GPU (the FP64 GEMM leaves the board at its power cap for seconds)
         secondary.append(run_workload("srht_c3", False, False, max(3, min(args.steps, 10)), max(3, args.warmup)))
         secondary[-1].pop("_host_block", None)
+        secondary[-1]["order"] = "timed before the primary workload"
+        time.sleep(1.0)
+    primary = run_workload(args.workload, not args.no_e2e, not args.no_cpu_baseline, args.steps, args.warmup)
+    host_block_np = primary.pop("_host_block", None)
 
     if not args.no_secondary and args.workload == "gauss_c2":
         # configs[4]: row-sharded range finder (sketch + NVLink peer-memory exchange + thin QR / SVD)

@@ -56,9 +56,10 @@ __device__ __forceinline__ int block_wait_ge(const int32_t *flag, int want, unsi
     if (threadIdx.x == 0) {
         int v = ld_acquire_gpu_i32(flag);
         if (v < want) {
-            const unsigned long long t0 = gtimer_ns();
+            // timeout on the SM-local cycle counter (cheap); 2 cycles per ns is an upper bound of the clock
+            const long long t0 = clock64(), limit = (long long)(2 * timeout_ns);
             while ((v = ld_acquire_gpu_i32(flag)) < want) {
-                if (gtimer_ns() - t0 > timeout_ns) { v = -1; break; }
+                if (clock64() - t0 > limit) { v = -1; break; }
             }
         }
         *s_slot = v;
@@ -350,22 +351,26 @@ __device__ __forceinline__ int jacobi_rotate(double *ap, double *aq, int64_t k, 
         a = fma(x.y, x.y, a); b = fma(y.y, y.y, b); g = fma(x.y, y.y, g);
     }
     a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
-    if (fabs(g) <= tol * sqrt(a * b) || g == 0.0) return 0;
-    const double zeta = (b - a) / (2.0 * g);
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+    if (g * g <= (tol * tol) * (a * b) || g == 0.0) return 0;
+    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (b - a) / (2 g), written with one
+    // square root and one division: t = sign(d h) |h| / (|d| + sqrt(d^2 + h^2)), d = b - a, h = 2 g
+    const double d = b - a, h = 2.0 * g;
+    const double r = sqrt(fma(d, d, h * h));
+    double t = fabs(h) / (fabs(d) + r);
+    if ((d < 0.0) != (h < 0.0)) t = -t;
+    const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
 #pragma unroll 4
     for (int64_t i = 2 * lane; i < k; i += 64) {
         const double2 x = *reinterpret_cast<const double2 *>(ap + i), y = *reinterpret_cast<const double2 *>(aq + i);
         *reinterpret_cast<double2 *>(ap + i) = make_double2(c * x.x - s * y.x, c * x.y - s * y.y);
         *reinterpret_cast<double2 *>(aq + i) = make_double2(s * x.x + c * y.x, s * x.y + c * y.y);
     }
-    if (vp) {
+    if (vp) {                                          // m is even and the V part is 16-byte aligned
 #pragma unroll 4
-        for (int64_t i = lane; i < m; i += 32) {
-            const double x = vp[i], y = vq[i];
-            vp[i] = c * x - s * y;
-            vq[i] = s * x + c * y;
+        for (int64_t i = 2 * lane; i < m; i += 64) {
+            const double2 x = *reinterpret_cast<const double2 *>(vp + i), y = *reinterpret_cast<const double2 *>(vq + i);
+            *reinterpret_cast<double2 *>(vp + i) = make_double2(c * x.x - s * y.x, c * x.y - s * y.y);
+            *reinterpret_cast<double2 *>(vq + i) = make_double2(s * x.x + c * y.x, s * x.y + c * y.y);
         }
     }
     return 1;
@@ -461,9 +466,9 @@ jacobi_block_kernel(double *A, int64_t k, int64_t lda, double *V, int64_t m,
                 __syncthreads();
                 if (tid == 0 || (tid == 32 && by >= 0)) {            // the two flags are polled concurrently
                     const int32_t *f = blkflag + (tid == 0 ? bx : by);
-                    const unsigned long long t0 = gtimer_ns();
+                    const long long t0 = clock64(), limit = (long long)(2 * timeout_ns);
                     while (ld_acquire_gpu_i32(f) < ground) {
-                        if (gtimer_ns() - t0 > timeout_ns) { s_slot = -1; break; }
+                        if (clock64() - t0 > limit) { s_slot = -1; break; }
                     }
                 }
                 __syncthreads();

@@ -73,10 +73,10 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(const PeerArgs a) {
     // 2. wait for every peer's partial of this epoch
     if (threadIdx.x < a.world) {
         const unsigned long long *mine = a.flags[a.rank] + threadIdx.x;
-        const unsigned long long t0 = globaltimer_ns();
+        // timeout on the SM-local cycle counter (2 cycles per ns bounds the clock from above)
+        const long long t0 = clock64(), limit = (long long)(2 * a.timeout_ns);
         while (ld_acquire_sys(mine) < a.epoch) {
-            if (globaltimer_ns() - t0 > a.timeout_ns) { s_fail = 1; break; }
-            __nanosleep(64);
+            if (clock64() - t0 > limit) { s_fail = 1; break; }
         }
     }
     __syncthreads();

@@ -56,6 +56,14 @@ def _worker(rank, world, port, n, k, seed, out):
         same *= float(all(torch.equal(g, ps) for g in gathered))     # bit-identical on every rank
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         red.close()
+        # odd k (scalar path of the exchange kernel), m = 1
+        red1 = PeerSketchReducer(1, k + 1)
+        p1 = sharding.srht_row_sharded(xs[:1], n, k + 1, seed, rank, world, reducer=red1).clone()
+        n1 = sharding.srht_row_sharded(xs[:1], n, k + 1, seed, rank, world)
+        same *= float(torch.equal(p1, n1) or float(((p1 - n1).norm() / n1.norm()).item()) < 1e-14)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        red1.check_status()
+        red1.close()
         if rank == 0:
             full = dense.embed_apply_rng(seed, 0, 1.0 / np.sqrt(k), k, torch.from_numpy(x).cuda())
             np.savez(out, yc=yc.cpu().numpy(), ys=ys.cpu().numpy(), yg=yg.cpu().numpy(), full=full.cpu().numpy(),
