@@ -232,9 +232,11 @@ int rla_residual_norm_f64(const double *S_dev, int64_t Q, int64_t k, int64_t r,
  * host, as in the reference; L and U are uploaded as CSR.
  * rla_sptrsv_plan_host (HOST arrays in and out, plain C++ on the CPU, once per factor): level of
  * every row (lower != 0: dependencies j < i; else j > i), the processing order of the rows
- * (order_out, inverse pos_out), the strictly triangular part re-packed as CSR with the entries of
- * a row sorted by the position of their column (rowptr2 n + 1, col2 / val2 up to nnz), the
- * diagonal (1.0 where absent), the GROUPS (group g = order positions [grp_start[g], grp_start[g] +
+ * (order_out, inverse pos_out), and -- ALL IN THAT ORDER, i.e. row p = row order_out[p] and
+ * external column indices replaced by positions -- the strictly triangular part re-packed as CSR
+ * (rowptr2 n + 1, col2 / val2 up to nnz, entries of a row sorted by column), the diagonal (1.0
+ * where absent) and split; the solve therefore works on X in schedule order (X[p] = row
+ * order_out[p], which rla_sptrsv_transpose_in/out produce with perm = pos[perm_r] etc.); the GROUPS (group g = order positions [grp_start[g], grp_start[g] +
  * grp_rows[g]), at most group_rows <= 32 rows that may depend on each other) and the STEPS:
  * kind 0 = one level of more than wide_min rows, order positions [step_lo, step_hi), rows
  * independent; kind 1 = groups [step_lo, step_hi), independent of each other (a band of
@@ -247,7 +249,8 @@ int rla_residual_norm_f64(const double *S_dev, int64_t Q, int64_t k, int64_t r,
  * factorisation applied on the way (perm_dev may be NULL): X[perm[i], c] = B[c, i] and
  * out[c, i] = X[perm[i], c].
  * rla_sptrsv_solve_f64: in-place T X = X, one or two launches per step (the step arrays stay on
- * the HOST); diag_dev NULL = unit diagonal; scratch_dev: rla_sptrsv_scratch_bytes(ldx, max_multi)
+ * the HOST); grp_of_pos_dev[p] = group of the row at order position p (n int32, -1 for rows of
+ * kind-0 steps); grp_start_host = host copy of grp_start, grp_csum_host = running sum of grp_rows (ngroups + 1 entries, host); diag_dev NULL = unit diagonal; scratch_dev: rla_sptrsv_scratch_bytes(ldx, max_multi)
  * bytes, zero-filled once by the caller. */
 int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val,
                          int lower, int wide_min, int group_rows, int max_multi,
@@ -262,12 +265,15 @@ int rla_sptrsv_transpose_out_f64(const double *x_dev, int64_t m, int64_t n, int6
                                  const int32_t *perm_dev, double *out_dev, int64_t ldo, void *stream);
 size_t rla_sptrsv_scratch_bytes(int64_t ldx, int max_multi);
 int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *col_dev, const double *val_dev,
-                         const double *diag_dev, const int32_t *order_dev, const int32_t *pos_dev,
-                         const int64_t *split_dev, const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
+                         const double *diag_dev, const int64_t *split_dev, const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
+                         const int32_t *grp_of_pos_dev, const int64_t *grp_start_host, const int64_t *grp_csum_host,
                          const int64_t *step_lo_host, const int64_t *step_mid_host, const int64_t *step_hi_host,
                          const int32_t *step_kind_host, int64_t nsteps, int max_multi,
                          double *x_dev, int64_t m, int64_t ldx,
                          void *scratch_dev, size_t scratch_bytes, void *stream);
+/* out[p, :] = in[map[p], :] on (n, ldx) blocks: re-ordering between the schedules of L and U */
+int rla_sptrsv_permute_rows_f64(const double *in_dev, const int32_t *map_dev, double *out_dev,
+                                int64_t n, int64_t ldx, void *stream);
 
 /* ------------------------------------------- row-sharded exchange (K5) -----
  * The one exchange step of the row-sharded sketch (no reference

@@ -63,52 +63,72 @@ __global__ void trsv_out_kernel(const double *__restrict__ X, int64_t m, int64_t
     }
 }
 
+// Everything the kernels touch is stored IN SCHEDULE ORDER: row p of X, rowptr, split, diag is the
+// p-th row of the processing order, and external column indices are positions too -- no
+// order / inverse-order indirection on the critical path of a launch.
+// out[p, :] = in[map[p], :]  (re-ordering of the block between the L and the U schedule)
+__global__ void trsv_permute_rows_kernel(const double *__restrict__ in, const int32_t *__restrict__ map,
+                                         double *__restrict__ out, int64_t n, int64_t ldx) {
+    const int64_t w2 = ldx / 2;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * w2; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = t / w2, c = 2 * (t - p * w2);
+        *reinterpret_cast<double2 *>(out + p * ldx + c) =
+            *reinterpret_cast<const double2 *>(in + (int64_t)map[p] * ldx + c);
+    }
+}
+
 struct TrsvArgs {
-    const int64_t *rowptr;      // CSR of the strictly triangular part, entries of a row sorted by the
-    const int32_t *col;         //   position of their column in the level order
+    const int64_t *rowptr;      // CSR of the strictly triangular part, rows and columns renumbered by
+    const int32_t *col;         //   schedule position, entries of a row sorted by column
     const double *val;
-    const double *diag;         // diagonal, or null for a unit diagonal
-    const int32_t *order;       // rows sorted by level
-    const int32_t *pos;         // inverse of order
+    const double *diag;         // diagonal by position, or null for a unit diagonal
     const int64_t *split;       // per row: first entry whose column lies in the row's own group
     double *X;
-    double *E;                  // scratch: external sums of the current group, TRSV_GROUP x ldx
-    unsigned int *counter;      // scratch: one arrival counter per chunk of right-hand sides (zero)
+    double *E;                  // scratch: external sums of the multi-row groups of a launch
+    unsigned int *counter;      // scratch: arrival counters (zero between launches)
     int64_t ldx, m;
 };
 
 constexpr int TRSV_GROUP = 32;                        // rows per group of the narrow tail
 
-constexpr int TRSV_WARPS = 16;                        // warps of a CTA that owns one row
+constexpr int TRSV_WARPS = 16;                        // warps of a CTA that owns one (long) row
+constexpr int TRSV_WARPS_SMALL = 4;                   // ... in steps of many short rows
 
 // -sum_e val[e] * X[col[e], c..c+1] over the entries [e0, e1) of one row, for warp `w` of `nw`
 // warps sharing the row.  A warp takes 32 consecutive entries at a time: (col, val) come in with
 // ONE coalesced load per lane and are broadcast by shuffles; the X rows are fetched 8 at a time
 // (8 independent 16-byte loads in flight per lane).  Every lane of the warp must call this.
+template <int INFLIGHT>
 __device__ __forceinline__ double2 row_sum_warp(const TrsvArgs &a, int64_t e0, int64_t e1, int64_t c, bool live,
                                                 int w, int nw) {
     const int lane = threadIdx.x & 31;
     double2 acc = make_double2(0.0, 0.0);
-    for (int64_t base = e0 + 32 * (int64_t)w; base < e1; base += 32 * (int64_t)nw) {
-        const int64_t e = base + lane;
-        int32_t jc = 0;
-        double vc = 0.0;
-        if (e < e1) { jc = a.col[e]; vc = a.val[e]; }
+    int64_t base = e0 + 32 * (int64_t)w;
+    int32_t jn = 0;
+    double vn = 0.0;
+    if (base + lane < e1) { jn = a.col[base + lane]; vn = a.val[base + lane]; }
+    for (; base < e1; base += 32 * (int64_t)nw) {
+        const int32_t jc = jn;
+        const double vc = vn;
+        // prefetch the (col, val) of this warp's next 32 entries while the X rows of these are fetched
+        const int64_t nb = base + 32 * (int64_t)nw + lane;
+        jn = 0; vn = 0.0;
+        if (nb < e1) { jn = a.col[nb]; vn = a.val[nb]; }
         const int cnt = (int)min((int64_t)32, e1 - base);
-        for (int t0 = 0; t0 < cnt; t0 += 8) {
-            int32_t j[8];
-            double v[8];
-            double2 x[8];
+        for (int t0 = 0; t0 < cnt; t0 += INFLIGHT) {    // INFLIGHT independent 16-byte loads in flight per lane
+            int32_t j[INFLIGHT];
+            double v[INFLIGHT];
+            double2 x[INFLIGHT];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < INFLIGHT; ++u) {
                 j[u] = __shfl_sync(0xffffffffu, jc, (t0 + u) & 31);
                 v[u] = __shfl_sync(0xffffffffu, vc, (t0 + u) & 31);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < INFLIGHT; ++u)
                 x[u] = (live && t0 + u < cnt) ? ldcg2(a.X + (int64_t)j[u] * a.ldx + c) : make_double2(0.0, 0.0);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < INFLIGHT; ++u) {
                 if (t0 + u < cnt) { acc.x = fma(-v[u], x[u].x, acc.x); acc.y = fma(-v[u], x[u].y, acc.y); }
             }
         }
@@ -124,8 +144,8 @@ trsv_wide_kernel(const TrsvArgs a, int64_t lo, int64_t hi) {
     if (idx >= hi) return;                             // whole warp
     const int64_t c = (int64_t)blockIdx.y * TRSV_RHS + 2 * lane;
     const bool live = c < a.ldx;
-    const int64_t i = a.order[idx];
-    double2 acc = row_sum_warp(a, a.rowptr[i], a.rowptr[i + 1], c, live, 0, 1);
+    const int64_t i = idx;
+    double2 acc = row_sum_warp<8>(a, a.rowptr[i], a.rowptr[i + 1], c, live, 0, 1);
     if (live) {
         double *xi = a.X + i * a.ldx + c;
         const double2 b = *reinterpret_cast<const double2 *>(xi);
@@ -137,50 +157,51 @@ trsv_wide_kernel(const TrsvArgs a, int64_t lo, int64_t hi) {
 
 // the same sum with the row split over the TRSV_WARPS warps of the CTA, combined in warp order;
 // result valid in warp 0
+template <int NW>
 __device__ __forceinline__ double2 row_sum_cta(const TrsvArgs &a, int64_t e0, int64_t e1, int64_t c, bool live,
                                                double2 (*part)[32]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double2 acc = row_sum_warp(a, e0, e1, c, live, warp, TRSV_WARPS);
+    double2 acc = row_sum_warp<(NW >= 16 ? 16 : 8)>(a, e0, e1, c, live, warp, NW);
     part[warp][lane] = acc;
     __syncthreads();
     if (warp == 0) {
         acc = part[0][lane];
 #pragma unroll
-        for (int w = 1; w < TRSV_WARPS; ++w) { acc.x += part[w][lane].x; acc.y += part[w][lane].y; }
+        for (int w = 1; w < NW; ++w) { acc.x += part[w][lane].x; acc.y += part[w][lane].y; }
     }
     return acc;
 }
 
 // One STEP of the schedule: a set of independent GROUPS.  A group is up to 32 rows that depend on
 // each other (a chain of consecutive levels inside one supernode of the factor) and, outside the
-// group, only on rows solved by earlier launches.  blockIdx.z = group, blockIdx.x = row of the
-// group, blockIdx.y = chunk of right-hand sides.  CTA (r, chunk, g) sums the EXTERNAL entries of
+// group, only on rows solved by earlier launches.  blockIdx.x = row (of some group of the launch),
+// blockIdx.y = chunk of right-hand sides.  CTA (r, chunk, g) sums the EXTERNAL entries of
 // its row with all its warps; a single-row group is finished right there; otherwise the last CTA
 // of the group to arrive (ticket counter, no spin-wait) stages the group's internal entries and
 // right-hand sides in shared memory and resolves the internal dependencies sequentially (one
 // warp, lanes = right-hand sides).  One launch per ~32 levels instead of one per level.
-constexpr int TRSV_INT_MAX = TRSV_GROUP * (TRSV_GROUP - 1) / 2;
-__global__ void __launch_bounds__(32 * TRSV_WARPS)
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, NW >= 16 ? 1 : 8)
 trsv_groups_kernel(const TrsvArgs a, const int64_t *__restrict__ grp_start, const int32_t *__restrict__ grp_rows,
-                   int64_t g_first) {
-    __shared__ double2 part[TRSV_WARPS][32];
-    __shared__ double2 xs[TRSV_GROUP][32];
-    __shared__ double2 rhs[TRSV_GROUP][32];
-    __shared__ int s_start[TRSV_GROUP + 1];
+                   const int32_t *__restrict__ grp_of_pos, int64_t g_first, int64_t p_first) {
+    __shared__ double2 part[NW][32];
+    __shared__ double2 xs[2][32];                      // x of the row just resolved, double buffered
+    __shared__ double D[TRSV_GROUP][TRSV_GROUP + 1];   // dense image of the group's internal entries
     __shared__ double s_diag[TRSV_GROUP];
-    __shared__ int s_icol[TRSV_INT_MAX];
-    __shared__ double s_ival[TRSV_INT_MAX];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t gid = g_first + blockIdx.z;
+    // CTA <-> one row: order position p_first + blockIdx.x (the rows of the groups of a launch are
+    // contiguous in the order), no idle CTAs
+    const int64_t p = p_first + blockIdx.x;
+    const int64_t gid = grp_of_pos[p];
     const int nrows = grp_rows[gid];
-    const int r = blockIdx.x;
-    if (r >= nrows) return;
     const int64_t g0 = grp_start[gid];
+    const int r = (int)(p - g0);
+    const int64_t eslot = gid - g_first;               // multi-row groups of a launch: scratch slot
     const int64_t c = (int64_t)blockIdx.y * TRSV_RHS + 2 * lane;
     const bool live = c < a.ldx;
-    const int64_t i = a.order[g0 + r];
-    double2 acc = row_sum_cta(a, a.rowptr[i], a.split[i], c, live, part);
+    const int64_t i = p;
+    double2 acc = row_sum_cta<NW>(a, a.rowptr[i], a.split[i], c, live, part);
     if (nrows == 1) {                                  // nothing internal: finish the row here
         if (warp == 0 && live) {
             double *xi = a.X + i * a.ldx + c;
@@ -191,69 +212,68 @@ trsv_groups_kernel(const TrsvArgs a, const int64_t *__restrict__ grp_start, cons
         }
         return;
     }
-    // groups of a step that have internal work are numbered 0.. in launch order: blockIdx.z
-    double *E = a.E + (int64_t)blockIdx.z * TRSV_GROUP * a.ldx;
-    unsigned int *counter = a.counter + (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
-    if (warp == 0 && live) *reinterpret_cast<double2 *>(E + (int64_t)r * a.ldx + c) = acc;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicAdd(counter, 1u);
-        s_last = ticket == (unsigned int)nrows - 1;
-        if (s_last) *counter = 0;                      // ready for the next launch
+    double *E = a.E + eslot * TRSV_GROUP * a.ldx;
+    unsigned int *counter = a.counter + eslot * gridDim.y + blockIdx.y;
+    if (warp == 0) {                                   // the writers fence, then one thread takes the ticket
+        if (live) *reinterpret_cast<double2 *>(E + (int64_t)r * a.ldx + c) = acc;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned int ticket = atomicAdd(counter, 1u);
+            s_last = ticket == (unsigned int)nrows - 1;
+            if (s_last) {
+                *counter = 0;                          // ready for the next launch
+                __threadfence();
+            }
+        }
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
-    // stage: internal entries (slot, value) of every row, and b + external sum of every row
-    if (warp == 0) {                                   // offsets of the rows' internal entries: warp scan
-        int cnt = 0;
-        if (lane < nrows) {
-            const int64_t iq = a.order[g0 + lane];
-            cnt = (int)(a.rowptr[iq + 1] - a.split[iq]);
-            s_diag[lane] = a.diag ? a.diag[iq] : 1.0;
-        }
-        int incl = cnt;
+    // Stage the group: its internal entries as a dense 32 x 32 lower-triangular image D, and
+    // b + external sum of the two rows (warp, warp + 16) this warp owns, in registers.
+    constexpr int RPW = TRSV_GROUP / NW;               // rows of the group per warp: q = warp + h * NW
+    for (int t = threadIdx.x; t < TRSV_GROUP * (TRSV_GROUP + 1); t += blockDim.x) (&D[0][0])[t] = 0.0;
+    if (threadIdx.x < nrows) s_diag[threadIdx.x] = a.diag ? a.diag[g0 + threadIdx.x] : 1.0;
+    __syncthreads();
+    double2 acc2[RPW];
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += t;
-        }
-        if (lane == 0) s_start[0] = 0;
-        if (lane < nrows) s_start[lane + 1] = incl;
-    }
-    __syncthreads();
-    for (int q = warp; q < nrows; q += TRSV_WARPS) {
-        const int64_t iq = a.order[g0 + q];
-        const int64_t e0 = a.split[iq];
-        const int cnt = s_start[q + 1] - s_start[q];
-        for (int t = lane; t < cnt; t += 32) {
-            s_icol[s_start[q] + t] = a.col[e0 + t];
-            s_ival[s_start[q] + t] = a.val[e0 + t];
-        }
-        if (live) {
-            const double2 b = ldcg2(a.X + iq * a.ldx + c), ext = ldcg2(E + (int64_t)q * a.ldx + c);
-            rhs[q][lane] = make_double2(b.x + ext.x, b.y + ext.y);
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {                                   // whole warp (idle lanes compute on zeros, never stored)
-        for (int q = 0; q < nrows; ++q) {
-            double2 sum = live ? rhs[q][lane] : make_double2(0.0, 0.0);
-            for (int t = s_start[q]; t < s_start[q + 1]; ++t) {
-                const double v = s_ival[t];
-                const double2 x = xs[s_icol[t]][lane];
-                sum.x = fma(-v, x.x, sum.x); sum.y = fma(-v, x.y, sum.y);
+    for (int h = 0; h < RPW; ++h) {
+        const int q = warp + h * NW;
+        acc2[h] = make_double2(0.0, 0.0);
+        if (q < nrows) {
+            const int64_t iq = g0 + q;
+            const int64_t e0 = a.split[iq];
+            const int cnt = (int)(a.rowptr[iq + 1] - e0);
+            for (int t = lane; t < cnt; t += 32) D[q][a.col[e0 + t]] = a.val[e0 + t];
+            if (live) {
+                const double2 b = ldcg2(a.X + iq * a.ldx + c), ext = ldcg2(E + (int64_t)q * a.ldx + c);
+                acc2[h] = make_double2(b.x + ext.x, b.y + ext.y);
             }
-            if (a.diag) { const double d = s_diag[q]; sum.x /= d; sum.y /= d; }
-            xs[q][lane] = sum;
-            __syncwarp();
         }
     }
     __syncthreads();
-    if (live)
-        for (int q = warp; q < nrows; q += TRSV_WARPS)
-            *reinterpret_cast<double2 *>(a.X + (int64_t)a.order[g0 + q] * a.ldx + c) = xs[q][lane];
+    // Right-looking resolve: row q becomes final, every later row subtracts its entry (r, q) times
+    // x_q.  One CTA barrier per row, rows spread over the warps, lanes = right-hand sides.
+    for (int q = 0; q < nrows; ++q) {
+        if ((q % NW) == warp) {
+            double2 x = acc2[0];                       // acc2[q / NW] with static register indices
+#pragma unroll
+            for (int h = 1; h < RPW; ++h) if (q >= h * NW) x = acc2[h];
+            if (a.diag) { const double d = s_diag[q]; x.x /= d; x.y /= d; }
+            xs[q & 1][lane] = x;
+            if (live) *reinterpret_cast<double2 *>(a.X + (g0 + q) * a.ldx + c) = x;
+        }
+        __syncthreads();
+        const double2 x = xs[q & 1][lane];
+#pragma unroll
+        for (int h = 0; h < RPW; ++h) {
+            const int r2 = warp + h * NW;
+            if (r2 > q && r2 < nrows) {
+                const double v = D[r2][q];
+                acc2[h].x = fma(-v, x.x, acc2[h].x); acc2[h].y = fma(-v, x.y, acc2[h].y);
+            }
+        }
+    }
 }
 
 }  // namespace rla
@@ -402,27 +422,28 @@ extern "C" int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int3
     }
     *nsteps_out = ns;
     *ngroups_out = ng;
-    // strictly triangular CSR with entries sorted by the position of their column
+    // strictly triangular CSR IN SCHEDULE ORDER: row p = row order[p], external columns = positions
     std::vector<std::pair<int32_t, int64_t>> tmp;
     int64_t w = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        rowptr2[i] = w;
-        diag_out[i] = 1.0;
+    for (int64_t p = 0; p < n; ++p) {
+        const int64_t i = order_out[p];
+        rowptr2[p] = w;
+        diag_out[p] = 1.0;
         tmp.clear();
         for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
-            if (col[e] == i) { diag_out[i] = val[e]; continue; }
+            if (col[e] == i) { diag_out[p] = val[e]; continue; }
             tmp.emplace_back(pos_out[col[e]], e);
         }
         std::sort(tmp.begin(), tmp.end());
-        const int64_t gs = gstart_of_pos[pos_out[i]];
+        const int64_t gs = gstart_of_pos[p];
         int64_t sp = -1;
         for (const auto &pe : tmp) {
             if (sp < 0 && gs >= 0 && pe.first >= gs) sp = w;
-            col2[w] = sp >= 0 ? (int32_t)(pe.first - gs) : col[pe.second];   // internal: slot inside the group
+            col2[w] = sp >= 0 ? (int32_t)(pe.first - gs) : pe.first;   // internal: slot inside the group
             val2[w] = val[pe.second];
             ++w;
         }
-        split_out[i] = sp < 0 ? w : sp;
+        split_out[p] = sp < 0 ? w : sp;
     }
     rowptr2[n] = w;
     return RLA_OK;
@@ -463,16 +484,16 @@ extern "C" size_t rla_sptrsv_scratch_bytes(int64_t ldx, int max_multi) {
 }
 
 extern "C" int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *col_dev, const double *val_dev,
-                                    const double *diag_dev, const int32_t *order_dev, const int32_t *pos_dev,
-                                    const int64_t *split_dev, const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
+                                    const double *diag_dev, const int64_t *split_dev, const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
+                                    const int32_t *grp_of_pos_dev, const int64_t *grp_start_host, const int64_t *grp_csum_host,
                                     const int64_t *step_lo, const int64_t *step_mid, const int64_t *step_hi,
                                     const int32_t *step_kind, int64_t nsteps, int max_multi,
                                     double *x_dev, int64_t m, int64_t ldx,
                                     void *scratch_dev, size_t scratch_bytes, void *stream) {
     RLA_REQUIRE(nsteps >= 0 && m >= 0 && ldx >= m && (ldx & 1) == 0 && max_multi >= 1, "rla_sptrsv_solve_f64: bad sizes");
     if (nsteps == 0 || m == 0) return RLA_OK;
-    RLA_REQUIRE(rowptr_dev && col_dev && val_dev && order_dev && pos_dev && split_dev && grp_start_dev && grp_rows_dev &&
-                step_lo && step_mid && step_hi && step_kind && x_dev && scratch_dev, "rla_sptrsv_solve_f64: null pointer");
+    RLA_REQUIRE(rowptr_dev && col_dev && val_dev && split_dev && grp_start_dev && grp_rows_dev &&
+                grp_of_pos_dev && grp_start_host && grp_csum_host && step_lo && step_mid && step_hi && step_kind && x_dev && scratch_dev, "rla_sptrsv_solve_f64: null pointer");
     RLA_REQUIRE(((uintptr_t)x_dev & 15) == 0 && ((uintptr_t)scratch_dev & 15) == 0,
                 "rla_sptrsv_solve_f64: X and scratch must be 16-byte aligned");
     if (scratch_bytes < rla_sptrsv_scratch_bytes(ldx, max_multi))
@@ -480,7 +501,7 @@ extern "C" int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *co
     cudaStream_t st = (cudaStream_t)stream;
     double *E = static_cast<double *>(scratch_dev);
     unsigned int *counter = reinterpret_cast<unsigned int *>(E + (size_t)max_multi * TRSV_GROUP * ldx);
-    TrsvArgs a = {rowptr_dev, col_dev, val_dev, diag_dev, order_dev, pos_dev, split_dev, x_dev, E, counter, ldx, m};
+    TrsvArgs a = {rowptr_dev, col_dev, val_dev, diag_dev, split_dev, x_dev, E, counter, ldx, m};
     const unsigned chunks = (unsigned)((ldx + TRSV_RHS - 1) / TRSV_RHS);
     RLA_REQUIRE(chunks <= 65535, "rla_sptrsv_solve_f64: too many right-hand sides");
     for (int64_t s = 0; s < nsteps; ++s) {
@@ -495,17 +516,38 @@ extern "C" int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *co
         const int64_t nmulti = step_mid[s] - step_lo[s], nsingle = step_hi[s] - step_mid[s];
         RLA_REQUIRE(nmulti >= 0 && nsingle >= 0 && nmulti <= max_multi && nsingle <= 65535 && nmulti + nsingle >= 1,
                     "rla_sptrsv_solve_f64: bad step %lld", (long long)s);
-        if (nmulti > 0) {
-            dim3 grid(TRSV_GROUP, chunks, (unsigned)nmulti);
-            trsv_groups_kernel<<<grid, 32 * TRSV_WARPS, 0, st>>>(a, grp_start_dev, grp_rows_dev, step_lo[s]);
-            count_launch();
-        }
-        if (nsingle > 0) {
-            dim3 grid(1, chunks, (unsigned)nsingle);
-            trsv_groups_kernel<<<grid, 32 * TRSV_WARPS, 0, st>>>(a, grp_start_dev, grp_rows_dev, step_mid[s]);
+        // the rows of the groups of a step are contiguous in the order: multi-row groups first
+        // (grp_csum_host = running sum of grp_rows, ngroups + 1 entries), then the single rows
+        const int64_t p0 = grp_start_host[step_lo[s]];
+        const int64_t rows_multi = grp_csum_host[step_mid[s]] - grp_csum_host[step_lo[s]];
+        {
+            const int64_t rows = rows_multi + nsingle;
+            dim3 grid((unsigned)rows, chunks);                        // one launch: multi-row groups, then single rows
+            // few rows (near the root of the elimination tree, long rows): 16 warps share a row;
+            // many rows (short): 4 warps per row so that every CTA of the step is resident at once
+            if (rows < 1024)
+                trsv_groups_kernel<TRSV_WARPS><<<grid, 32 * TRSV_WARPS, 0, st>>>(a, grp_start_dev, grp_rows_dev,
+                                                                                grp_of_pos_dev, step_lo[s], p0);
+            else
+                trsv_groups_kernel<TRSV_WARPS_SMALL><<<grid, 32 * TRSV_WARPS_SMALL, 0, st>>>(
+                    a, grp_start_dev, grp_rows_dev, grp_of_pos_dev, step_lo[s], p0);
             count_launch();
         }
     }
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
+
+// out[p, :] = in[map[p], :] on (n, ldx) blocks: the re-ordering between the schedules of L and U
+extern "C" int rla_sptrsv_permute_rows_f64(const double *in_dev, const int32_t *map_dev, double *out_dev, int64_t n,
+                                           int64_t ldx, void *stream) {
+    RLA_REQUIRE(n >= 0 && ldx >= 0 && (ldx & 1) == 0, "rla_sptrsv_permute_rows_f64: bad sizes");
+    if (n == 0 || ldx == 0) return RLA_OK;
+    RLA_REQUIRE(in_dev && map_dev && out_dev && in_dev != out_dev, "rla_sptrsv_permute_rows_f64: bad pointers");
+    const int64_t work = n * (ldx / 2);
+    const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, (int64_t)sm_count() * 16);
+    trsv_permute_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in_dev, map_dev, out_dev, n, ldx);
+    count_launch();
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;
 }

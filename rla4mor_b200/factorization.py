@@ -98,12 +98,23 @@ class TriangularFactor:
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
         self.rowptr, self.col, self.val = dev(p["rowptr"]), dev(p["col"]), dev(p["val"])
         self.diag = None if unit_diagonal else dev(p["diag"])
-        self.order, self.pos, self.split = dev(p["order"]), dev(p["pos"]), dev(p["split"])
+        self.order_host, self.pos_host = p["order"], p["pos"]            # schedule order (host): X[p] = row order[p]
+        self.split = dev(p["split"])
         self.grp_start, self.grp_rows = dev(p["grp_start"]), dev(p["grp_rows"])
+        ng = self.ngroups
+        gop = np.full(max(self.n, 1), -1, dtype=np.int32)              # group of the row at every order position
+        if ng:
+            gs, gr = p["grp_start"][:ng], p["grp_rows"][:ng]
+            gop[np.repeat(gs, gr) + (np.arange(int(gr.sum())) - np.repeat(np.cumsum(gr) - gr, gr))] = \
+                np.repeat(np.arange(ng, dtype=np.int32), gr)
+        self.grp_of_pos = dev(gop)
+        self.grp_start_host = np.ascontiguousarray(p["grp_start"][:max(ng, 1)], dtype=np.int64)
+        self.grp_csum_host = np.ascontiguousarray(np.concatenate([[0], np.cumsum(p["grp_rows"][:ng])]), dtype=np.int64)
         self._scratch = {}
 
     def solve_inplace(self, X, m):
-        """T X = X on the (n, ldx) device block with the m right-hand sides contiguous."""
+        """T X = X on the (n, ldx) device block with the m right-hand sides contiguous, rows in
+        SCHEDULE order: X[p] belongs to row order_host[p] of T."""
         import torch
         ldx = X.stride(0)
         key = (ldx, X.device.index)
@@ -112,9 +123,10 @@ class TriangularFactor:
                                              device=X.device)
         sc = self._scratch[key]
         check(lib().rla_sptrsv_solve_f64(self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
-                                         None if self.diag is None else self.diag.data_ptr(), self.order.data_ptr(),
-                                         self.pos.data_ptr(), self.split.data_ptr(), self.grp_start.data_ptr(),
-                                         self.grp_rows.data_ptr(), self.step_lo.ctypes.data, self.step_mid.ctypes.data,
+                                         None if self.diag is None else self.diag.data_ptr(),
+                                         self.split.data_ptr(), self.grp_start.data_ptr(),
+                                         self.grp_rows.data_ptr(), self.grp_of_pos.data_ptr(),
+                                         self.grp_start_host.ctypes.data, self.grp_csum_host.ctypes.data, self.step_lo.ctypes.data, self.step_mid.ctypes.data,
                                          self.step_hi.ctypes.data, self.step_kind.ctypes.data, self.nsteps,
                                          self.max_multi, X.data_ptr(), int(m), ldx, sc.data_ptr(), sc.numel(),
                                          stream_ptr()), "rla_sptrsv_solve_f64")
@@ -131,21 +143,34 @@ class SparseLU:
         L, U = factorization.L, factorization.U
         assert not np.iscomplexobj(L.data) and not np.iscomplexobj(U.data), "real factorisations only"
         self._L, self._U = L.tocsr(), U.tocsr()
-        self.perm_r = torch.from_numpy(np.ascontiguousarray(factorization.perm_r, dtype=np.int32)).to(self.device)
-        self.perm_c = torch.from_numpy(np.ascontiguousarray(factorization.perm_c, dtype=np.int32)).to(self.device)
+        self._perm_r = np.ascontiguousarray(factorization.perm_r, dtype=np.int64)
+        self._perm_c = np.ascontiguousarray(factorization.perm_c, dtype=np.int64)
         self._fwd = None
         self._adj = None
 
     def _factors(self, adjoint):
+        """(first factor, second factor, perm_in, map_mid, perm_out): the block goes in with
+        X1[perm_in[i]] = b[i] (first factor's schedule order), is re-ordered X2[p] = X1[map_mid[p]] into the
+        second factor's order, and comes out as x[i] = X2[perm_out[i]]."""
+        import torch
+        cached = self._adj if adjoint else self._fwd
+        if cached is not None:
+            return cached
         if not adjoint:
-            if self._fwd is None:
-                self._fwd = (TriangularFactor(self._L, True, True, self.device),
-                             TriangularFactor(self._U, False, False, self.device))
-            return self._fwd
-        if self._adj is None:
-            self._adj = (TriangularFactor(self._U.T.tocsr(), True, False, self.device),
-                         TriangularFactor(self._L.T.tocsr(), False, True, self.device))
-        return self._adj
+            f1 = TriangularFactor(self._L, True, True, self.device)
+            f2 = TriangularFactor(self._U, False, False, self.device)
+            p_in, p_out = self._perm_r, self._perm_c
+        else:
+            f1 = TriangularFactor(self._U.T.tocsr(), True, False, self.device)
+            f2 = TriangularFactor(self._L.T.tocsr(), False, True, self.device)
+            p_in, p_out = self._perm_c, self._perm_r
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
+        res = (f1, f2, dev(f1.pos_host[p_in]), dev(f1.pos_host[f2.order_host]), dev(f2.pos_host[p_out]))
+        if adjoint:
+            self._adj = res
+        else:
+            self._fwd = res
+        return res
 
     def solve(self, B, adjoint=False):
         """(m, n) block of right-hand sides (one per row) -> (m, n) block of solutions of
@@ -159,16 +184,18 @@ class SparseLU:
         out = torch.empty((m, self.n), dtype=torch.float64, device=B.device)
         if m == 0 or self.n == 0:
             return out
-        first, second = self._factors(adjoint)
-        p_in, p_out = (self.perm_c, self.perm_r) if adjoint else (self.perm_r, self.perm_c)
+        first, second, p_in, p_mid, p_out = self._factors(adjoint)
         ldx = m + (m & 1)
         with torch.cuda.device(B.device):
-            X = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
+            X1 = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
+            X2 = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
             check(lib().rla_sptrsv_transpose_in_f64(B.data_ptr(), m, self.n, B.stride(0), p_in.data_ptr(),
-                                                    X.data_ptr(), ldx, stream_ptr()), "rla_sptrsv_transpose_in_f64")
-            first.solve_inplace(X, m)
-            second.solve_inplace(X, m)
-            check(lib().rla_sptrsv_transpose_out_f64(X.data_ptr(), m, self.n, ldx, p_out.data_ptr(),
+                                                    X1.data_ptr(), ldx, stream_ptr()), "rla_sptrsv_transpose_in_f64")
+            first.solve_inplace(X1, m)
+            check(lib().rla_sptrsv_permute_rows_f64(X1.data_ptr(), p_mid.data_ptr(), X2.data_ptr(), self.n, ldx,
+                                                    stream_ptr()), "rla_sptrsv_permute_rows_f64")
+            second.solve_inplace(X2, m)
+            check(lib().rla_sptrsv_transpose_out_f64(X2.data_ptr(), m, self.n, ldx, p_out.data_ptr(),
                                                      out.data_ptr(), out.stride(0), stream_ptr()),
                   "rla_sptrsv_transpose_out_f64")
         return out

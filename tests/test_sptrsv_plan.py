@@ -17,14 +17,15 @@ def _fem(nx):
 
 
 def _replay(p, B, unit):
-    """What trsv_wide_kernel / trsv_groups_kernel compute, step by step."""
-    X = B.copy()
-    rowptr, col, val, order, split, pos = p["rowptr"], p["col"], p["val"], p["order"], p["split"], p["pos"]
+    """What trsv_wide_kernel / trsv_groups_kernel compute, step by step, in schedule order:
+    X[q] is row order[q]; external column indices are positions, internal ones slots."""
+    rowptr, col, val, order, split = p["rowptr"], p["col"], p["val"], p["order"], p["split"]
+    X = B[order].copy()
     done = np.zeros(p["n"], dtype=bool)
     for lo, mid, hi, kind in zip(p["step_lo"], p["step_mid"], p["step_hi"], p["step_kind"]):
         new = {}
         if kind == 0:
-            for i in order[lo:hi]:
+            for i in range(lo, hi):
                 e0, e1 = rowptr[i], rowptr[i + 1]
                 assert split[i] == e1 and np.all(done[col[e0:e1]])        # only rows of earlier steps
                 new[i] = (X[i] - val[e0:e1] @ X[col[e0:e1]]) / (1.0 if unit else p["diag"][i])
@@ -33,9 +34,11 @@ def _replay(p, B, unit):
             for g in range(lo, hi):
                 g0, nr = p["grp_start"][g], p["grp_rows"][g]
                 assert 1 <= nr <= 32 and (nr > 1) == (g < mid)
-                rows = order[g0:g0 + nr]
+                if g > lo:
+                    assert g0 == p["grp_start"][g - 1] + p["grp_rows"][g - 1]   # a step is contiguous in the order
                 xs = np.zeros((nr,) + X.shape[1:])
-                for q, i in enumerate(rows):
+                for q in range(nr):
+                    i = g0 + q
                     e0, sp, e1 = rowptr[i], split[i], rowptr[i + 1]
                     assert np.all(done[col[e0:sp]])                       # external: earlier steps only
                     assert np.all(col[sp:e1] < q)                         # internal: earlier slots of the group
@@ -46,7 +49,9 @@ def _replay(p, B, unit):
             X[i] = v
             done[i] = True
     assert done.all()
-    return X
+    out = np.empty_like(X)
+    out[order] = X
+    return out
 
 
 @pytest.mark.parametrize("nx", [7, 40])
