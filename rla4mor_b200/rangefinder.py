@@ -47,8 +47,9 @@ def sketch_svd(S, want_v=True, precondition=None, qr=None):
     (reductor_ops.svd_jacobi's convention).
 
     For k >= 2m the Jacobi iteration runs on the m x m triangular factor instead of the m x k
-    sketch (QR preconditioning): S = R^T Q (Gram-Schmidt), R^T = W^T diag(s) Z (block Jacobi on
-    rows of length m), U_rows = Z Q.  Rows four times shorter at BASELINE configs[4]."""
+    sketch (QR preconditioning): S = R^T Q (Gram-Schmidt), R = W^T diag(s) Z (block Jacobi on the
+    rows of R, length m), S = Z^T diag(s) (W Q).  Rows four times shorter at BASELINE configs[4]
+    and fewer sweeps."""
     m, k = S.shape
     if precondition is None:
         precondition = k >= 2 * m and m >= 16
@@ -56,10 +57,19 @@ def sketch_svd(S, want_v=True, precondition=None, qr=None):
         return ops.svd_jacobi(S, want_v=want_v)
     Q, R = ops.gram_schmidt(S) if qr is None else qr    # S = R^T Q, R (m', m) with m' <= m kept rows
     mk = R.shape[0]
-    M = torch.zeros((m, mk + (mk & 1)), dtype=torch.float64, device=S.device)
-    M[:, :mk] = R.T
-    Z, s, W = ops.svd_jacobi(M, want_v=want_v)
-    return ops.gemm_nn(Z[:, :mk], Q), s, W
+    # Jacobi on the ROWS OF R (Gram matrix R R^T, one QR-iteration step closer to diagonal than
+    # S S^T = R^T R -- this is what makes the QR a preconditioner): W R = diag(s) Z, hence
+    # S = R^T Q = Z^T diag(s) (W Q): left factor Z, right factor W Q.
+    M = torch.zeros((mk, m + (m & 1)), dtype=torch.float64, device=S.device)
+    M[:, :m] = R
+    Z, s, W = ops.svd_jacobi(M, want_v=True)            # rows of Z: normalised rotated rows of R
+    Urows = ops.gemm_nn(W, Q)                           # (m', m') @ (m', k)
+    Zm = Z[:, :m]
+    if mk < m:                                          # rank-deficient: pad with zero singular values
+        s = torch.cat([s, torch.zeros(m - mk, dtype=s.dtype, device=s.device)])
+        Urows = torch.cat([Urows, torch.zeros((m - mk, k), dtype=Urows.dtype, device=Urows.device)])
+        Zm = torch.cat([Zm, torch.zeros((m - mk, m), dtype=Zm.dtype, device=Zm.device)])
+    return Urows, s, (Zm if want_v else None)
 
 
 def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, group=None, svd=True, reducer=None):

@@ -8,6 +8,7 @@ import scipy.sparse as sp
 from scipy.sparse.linalg import splu
 
 from golden_util import rel_fro
+from oracle import factorization_oracle as fo
 
 pytestmark = pytest.mark.gpu
 
@@ -34,7 +35,7 @@ def test_inverse_lu_operator_matches_superlu(rb, nx, m):
     inv = InverseLuOperator(op)                                   # general splu (COLAMD, partial pivoting)
     V = np.random.RandomState(nx).standard_normal((m, n))
     got = inv.apply(op.source.from_numpy(V)).to_numpy()
-    ref = inv.factorization.solve(V.T).T                          # the reference's own expression
+    ref = fo.inverse_lu_apply(inv.factorization, V)               # the reference's own expression (:118-124)
     assert rel_fro(got, ref) < 1e-12
     assert rel_fro((A @ got.T).T, V) < 1e-11
     # apply_inverse applies the matrix itself (:134-135)
@@ -49,21 +50,22 @@ def test_inverse_lu_adjoint_nonsymmetric_and_symmetric_mode(rb):
     op = rb.MatrixOperator(A)
     inv = InverseLuOperator(op)
     V = rs.standard_normal((7, n))
-    assert rel_fro(inv.apply(op.source.from_numpy(V)).to_numpy(), inv.factorization.solve(V.T).T) < 1e-12
+    assert rel_fro(inv.apply(op.source.from_numpy(V)).to_numpy(), fo.inverse_lu_apply(inv.factorization, V)) < 1e-12
     got = inv.apply_adjoint(op.source.from_numpy(V)).to_numpy()
-    assert rel_fro(got, inv.factorization.solve(V.T, trans="H").T) < 1e-12
+    assert rel_fro(got, fo.inverse_lu_apply_adjoint(inv.factorization, V)) < 1e-12
     S = _fem(40)
     ops = rb.MatrixOperator(S)
     invs = InverseLuOperator(ops, symetric=True)                  # splu_symetric (:17-22)
     W = rs.standard_normal((12, S.shape[0]))
-    assert rel_fro(invs.apply(ops.source.from_numpy(W)).to_numpy(), splu_symetric(S).solve(W.T).T) < 1e-12
+    assert rel_fro(invs.apply(ops.source.from_numpy(W)).to_numpy(), fo.inverse_lu_apply(fo.factorize(S, symetric=True), W)) < 1e-12
 
 
 def test_cholesky_sqrt_product(rb):
     from rla4mor_b200.factorization import operator_to_cholesky, lu_to_cholesky
     S = _fem(30)
     Q = operator_to_cholesky(rb.MatrixOperator(S, source_id="S", range_id="S"))
-    Qh = lu_to_cholesky(S)
+    Qh = fo.lu_to_cholesky(S)
+    assert abs(lu_to_cholesky(S) - Qh).max() == 0.0               # host part of the product = the reference's lines
     assert abs(Qh.conj().T @ Qh - S).max() < 1e-12               # Q^H Q == matrix (:37)
     V = np.random.RandomState(0).standard_normal((6, S.shape[0]))
     got = Q.apply(Q.source.from_numpy(V)).to_numpy()
@@ -98,3 +100,22 @@ def test_sketched_reductor_with_inverse_product(rb):
         ref = eo.srht_apply(lu.solve((A @ U.T)).T, k, 2).T        # Theta R^-1 A_q U as a k x m matrix
         assert rel_fro(got.cpu().numpy(), ref) < 1e-10
     assert rel_fro(red.s_rhs[0].cpu().numpy(), eo.srht_apply(lu.solve(f[0]).reshape(1, -1), k, 2).reshape(-1)) < 1e-10
+
+
+def test_lu_solve_edge_cases(rb):
+    """Empty block, 1 x 1 and diagonal matrices (a single level), many right-hand sides (several
+    chunks of 64, odd count), a chain (every level one row: groups of 32)."""
+    import torch
+    from rla4mor_b200.factorization import InverseLuOperator
+    rs = np.random.RandomState(0)
+    for A in (sp.csc_matrix(np.array([[2.5]])), sp.diags(np.linspace(1.0, 3.0, 50)).tocsc(),
+              (sp.eye(200) * 3.0 + sp.diags([np.ones(199)], [-1]) + sp.diags([0.5 * np.ones(199)], [1])).tocsc()):
+        op = rb.MatrixOperator(A)
+        inv = InverseLuOperator(op)
+        n = A.shape[0]
+        for m in (0, 1, 131):
+            V = rs.standard_normal((m, n))
+            got = inv.apply(op.source.from_numpy(torch.from_numpy(V).cuda().reshape(m, n))).to_numpy()
+            assert got.shape == (m, n)
+            if m:
+                assert rel_fro(got, fo.inverse_lu_apply(inv.factorization, V)) < 1e-13

@@ -152,3 +152,21 @@ def test_gram_schmidt_and_reductor_identities():
     b = [rs.standard_normal((40, 1))]
     val = ro.residual_norm(S2, [0.5, 2.0], b, [1.0], a)
     assert np.isclose(val, np.linalg.norm(0.5 * S2[0] @ a + 2.0 * S2[1] @ a - b[0][:, 0]))
+
+
+def test_factorization_oracle_identities():
+    """oracle/factorization_oracle.py restates utilities/factorization.py:17-52,118-132 (SciPy
+    SuperLU, the reference's own dependency); pinned by A x = b, A^H x = b and Q^H Q = A."""
+    import scipy.sparse as sp
+    from oracle import factorization_oracle as fo
+    rs = np.random.RandomState(0)
+    n = 300
+    A = (sp.random(n, n, 0.02, random_state=rs) + 4.0 * sp.eye(n)).tocsc()
+    V = rs.standard_normal((5, n))
+    slu = fo.factorize(A)
+    assert np.linalg.norm((A @ fo.inverse_lu_apply(slu, V).T).T - V) / np.linalg.norm(V) < 1e-12
+    assert np.linalg.norm((A.T @ fo.inverse_lu_apply_adjoint(slu, V).T).T - V) / np.linalg.norm(V) < 1e-12
+    S = (A @ A.T + sp.eye(n)).tocsc()
+    Q = fo.lu_to_cholesky(S)
+    assert abs(Q.conj().T @ Q - S).max() < 1e-10
+    assert np.linalg.norm(fo.inverse_lu_apply(fo.factorize(S, symetric=True), V) @ S.T - V) / np.linalg.norm(V) < 1e-10
