@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -586,6 +587,14 @@ static GsCfg gs_config(int64_t r, int64_t k) {
     else if (ept <= 8) { rpc = 8; e = 8; }
     else if (ept <= 16) { rpc = 4; e = 16; }
     else return c;
+    // fewer rows per CTA = fewer dot products per step and CTA (the step is latency-bound), as long
+    // as the grid stays co-resident; RLA_GS_RPC overrides (development)
+    if (e <= 8) {
+        int want = r <= 128 ? 2 : 4;                   // measured: 256 x 1024 is fastest with 4 (re-iterations sum G partials)
+        if (const char *env = getenv("RLA_GS_RPC")) want = atoi(env);
+        for (int cand : {2, 4, 8})
+            if (cand >= want && (r + cand - 1) / cand <= sms) { rpc = cand; break; }
+    }
     const int64_t g = (r + rpc - 1) / rpc;
     if (g > sms) return c;
     c.rpc = rpc; c.ept = e; c.grid = (int)g;
@@ -637,8 +646,10 @@ extern "C" int rla_gram_schmidt_ws_f64(double *a, int64_t r, int64_t k, int64_t 
     void *args[] = {&a, &r, &k, &lda, &offset, &R, &flags, &atol, &rtol, &thr, &scratch, &coef, &ctrl, &done, &status,
                     &timeout_ns};
     const void *fn = nullptr;
-    if (c.rpc == 8 && c.ept == 4) fn = (const void *)gs_grid_kernel<8, 4>;
-    else if (c.rpc == 8 && c.ept == 8) fn = (const void *)gs_grid_kernel<8, 8>;
+    if (c.ept == 4) fn = c.rpc == 8 ? (const void *)gs_grid_kernel<8, 4> : c.rpc == 4 ? (const void *)gs_grid_kernel<4, 4>
+                                                                                    : (const void *)gs_grid_kernel<2, 4>;
+    else if (c.ept == 8) fn = c.rpc == 8 ? (const void *)gs_grid_kernel<8, 8> : c.rpc == 4 ? (const void *)gs_grid_kernel<4, 8>
+                                                                                         : (const void *)gs_grid_kernel<2, 8>;
     else fn = (const void *)gs_grid_kernel<4, 16>;
     // cooperative launch: guarantees that all CTAs are co-resident (they wait on each other's flags)
     RLA_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(c.grid), dim3(256), args, 0, st));
