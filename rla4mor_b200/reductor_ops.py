@@ -117,13 +117,17 @@ def _round_robin(m, keep_bye=False):
 _PAIRS = {}
 
 
-def svd_jacobi(S, want_v=False, max_sweeps=30, tol=1e-15, block=True):
+def svd_jacobi(S, want_v=False, max_sweeps=30, tol=None, block=True):
     """One-sided Jacobi SVD of the k x m sketch held as a row block S (m, k).
     Returns (U_rows (m, k) orthonormal rows, s (m,), V (m, m) or None), singular values
     sorted descending: S = (V^T diag(s) U_rows) in the row layout, i.e. the k x m matrix
     S^T = U_rows^T diag(s) V."""
     A = _rows(S).to(torch.float64).clone()
     m, k = A.shape
+    if tol is None:
+        # rows p, q count as orthogonal when |<a_p, a_q>| <= tol |a_p| |a_q|; a length-k dot product carries
+        # sqrt(k) * eps of rounding noise, below which rotations only chase noise (LAPACK xGESVJ: sqrt(m) * eps)
+        tol = max(1.0, np.sqrt(k)) * 1.1102230246251565e-16
     s = torch.empty((m,), dtype=torch.float64, device=A.device)
     V = torch.empty((m, m), dtype=torch.float64, device=A.device) if want_v else None
     B = lib().rla_svd_jacobi_block_rows(k, m, 1 if want_v else 0) if (block and A.data_ptr() % 16 == 0
