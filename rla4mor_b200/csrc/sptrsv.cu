@@ -389,6 +389,22 @@ extern "C" int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int3
                 if (comp_first[root] < 0) { comp_first[root] = (int32_t)multi.size(); multi.emplace_back(); }
                 multi[comp_first[root]].push_back((int32_t)t);
             }
+            // longest rows first: a step ends with its slowest CTA, so the long rows (ancestor
+            // separators) must start at once instead of queueing behind thousands of short ones
+            auto rowlen = [&](int32_t t) { const int64_t i = band_rows[t]; return rowptr[i + 1] - rowptr[i]; };
+            std::vector<int64_t> mlen(multi.size(), 0);
+            for (size_t g = 0; g < multi.size(); ++g)
+                for (int32_t t : multi[g]) mlen[g] = std::max(mlen[g], rowlen(t));
+            std::vector<size_t> mord(multi.size());
+            for (size_t g = 0; g < multi.size(); ++g) mord[g] = g;
+            std::stable_sort(mord.begin(), mord.end(), [&](size_t x, size_t y) { return mlen[x] > mlen[y]; });
+            {
+                std::vector<std::vector<int32_t>> sorted;
+                sorted.reserve(multi.size());
+                for (size_t g : mord) sorted.push_back(std::move(multi[g]));
+                multi.swap(sorted);
+            }
+            std::stable_sort(single.begin(), single.end(), [&](int32_t x, int32_t y) { return rowlen(x) > rowlen(y); });
             int64_t p = p0;
             size_t mi = 0, si = 0;
             // emit steps: at most max_multi multi-row groups (and at most 65535 groups) per step
