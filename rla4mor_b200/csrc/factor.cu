@@ -44,14 +44,9 @@ __device__ __forceinline__ void st_release_gpu_i32(int32_t *p, int v) {
 __device__ __forceinline__ void red_release_gpu_add(int32_t *p, int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long gtimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
-// Block-wide wait until *flag >= want (thread 0 polls with acquire loads; a wall-clock timeout
-// turns a protocol error into an error code instead of a hung GPU).  Returns the value seen,
+// Block-wide wait until *flag >= want (thread 0 polls with acquire loads; a timeout on the SM cycle
+// counter turns a protocol error into an error code instead of a hung GPU).  Returns the value seen,
 // or -1 on timeout.  All threads get the same result.
 __device__ __forceinline__ int block_wait_ge(const int32_t *flag, int want, unsigned long long timeout_ns, int *s_slot) {
     if (threadIdx.x == 0) {
