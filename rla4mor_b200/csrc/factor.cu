@@ -657,7 +657,9 @@ extern "C" int rla_gram_schmidt_ws_f64(double *a, int64_t r, int64_t k, int64_t 
 extern "C" int rla_svd_jacobi_block_rows(int64_t k, int64_t m, int want_v) {
     if (k < 2 || (k & 1) || m < 4 || (want_v && (m & 1)) || !coop_ok()) return 0;
     const int sms = sm_count();
-    for (int B = 8; B >= 2; B >>= 1) {
+    int bmax = 8;
+    if (const char *env = getenv("RLA_JACOBI_B")) bmax = std::max(2, std::min(8, atoi(env)));   // development
+    for (int B = bmax; B >= 2; B >>= 1) {
         const size_t smem = (size_t)2 * B * (size_t)((k + (want_v ? m : 0) + 3) & ~int64_t(1)) * sizeof(double);
         const int64_t nblk = (m + B - 1) / B;
         const int64_t npairs = (nblk + 1) / 2;

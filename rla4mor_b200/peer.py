@@ -99,7 +99,15 @@ class PeerSketchReducer:
         if int(self._status.item()) != 0:
             raise RlaError("rla_peer_allreduce_f64: a peer did not publish its partial sketch in time")
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def close(self):
+        """Collective: every rank must call it (peers unmap before the owner frees)."""
         import torch
         if self._own is None:
             return
