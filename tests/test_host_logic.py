@@ -62,6 +62,37 @@ def test_workspace_queries_and_argument_checks_without_gpu():
     assert lib.rla_embed_apply_rng_f64(0, 7, 1.0, 0, 4, 0, 64, None, 1, 64, None, 4, 0, None, 0, None) == -1
 
 
+def test_new_entry_points_validate_arguments_without_gpu():
+    """Argument checks of the factorisation / triangular-solve / peer-exchange entry points
+    happen on the host before any CUDA call."""
+    import ctypes
+    lib = rb.lib()
+    assert lib.rla_sptrsv_scratch_bytes(64, 256) >= 256 * 32 * 64 * 8
+    assert lib.rla_svd_jacobi_block_scratch_ints(256, 8, 30) == 30 + 32 + 8
+    assert lib.rla_svd_jacobi_block_rows(1024, 256, 1) in (0, 2, 4, 8)          # 0 without a device
+    # odd ldx / negative sizes / null pointers -> RLA_ERR_INVALID (-1), no device touched
+    assert lib.rla_sptrsv_transpose_in_f64(None, 3, 10, 10, None, None, 3, None) == -1
+    assert lib.rla_sptrsv_permute_rows_f64(None, None, None, 5, 3, None) == -1
+    assert lib.rla_trinv_upper_f64(None, 4, 2, None, 4, None) == -1
+    assert lib.rla_peer_allreduce_f64(None, None, 2, 0, 1, 4, 4, 4, None, None, 4, None, 1.0, None) == -1
+    one = (ctypes.c_void_p * 1)(8)
+    out = ctypes.c_void_p(16)
+    assert lib.rla_peer_allreduce_f64(one, one, 17, 0, 1, 4, 4, 4, None, out, 4, out, 1.0, None) == -1   # world > 16
+    assert b"world size" in lib.rla_last_error()
+    assert lib.rla_peer_allreduce_f64(one, one, 1, 0, 0, 4, 4, 4, None, out, 4, out, 1.0, None) == -1    # epoch 0
+    # the plan builder rejects entries on the wrong side of the diagonal
+    rowptr = np.array([0, 2, 3], dtype=np.int64); col = np.array([0, 1, 1], dtype=np.int32); val = np.ones(3)
+    bufs = [np.empty(4, dtype=np.int64) for _ in range(12)]
+    ns, ng, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
+    rc = lib.rla_sptrsv_plan_host(2, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, 1, 4096, 32, 256,
+                                  bufs[0].ctypes.data, bufs[1].ctypes.data, bufs[2].ctypes.data, bufs[3].ctypes.data,
+                                  bufs[4].ctypes.data, bufs[5].ctypes.data, bufs[6].ctypes.data, bufs[7].ctypes.data,
+                                  bufs[8].ctypes.data, bufs[9].ctypes.data, ctypes.byref(ng), bufs[10].ctypes.data,
+                                  bufs[11].ctypes.data, bufs[0].ctypes.data, bufs[1].ctypes.data, ctypes.byref(ns),
+                                  ctypes.byref(nl))
+    assert rc == -1 and b"wrong side" in lib.rla_last_error()
+
+
 def test_draws_match_reference_expressions():
     n, k, seed = 1000, 50, 4
     r, s = rb.draw_signs_and_indices(n, k, seed)
