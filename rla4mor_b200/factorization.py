@@ -117,7 +117,8 @@ class TriangularFactor:
         SCHEDULE order: X[p] belongs to row order_host[p] of T."""
         import torch
         ldx = X.stride(0)
-        key = (ldx, X.device.index)
+        # one scratch (external sums + ticket counters) per stream: solves on different streams never share it
+        key = (ldx, X.device.index, torch.cuda.current_stream(X.device).cuda_stream)
         if key not in self._scratch:
             self._scratch[key] = torch.zeros(lib().rla_sptrsv_scratch_bytes(ldx, self.max_multi), dtype=torch.uint8,
                                              device=X.device)
@@ -126,7 +127,8 @@ class TriangularFactor:
                                          None if self.diag is None else self.diag.data_ptr(),
                                          self.split.data_ptr(), self.grp_start.data_ptr(),
                                          self.grp_rows.data_ptr(), self.grp_of_pos.data_ptr(),
-                                         self.grp_start_host.ctypes.data, self.grp_csum_host.ctypes.data, self.step_lo.ctypes.data, self.step_mid.ctypes.data,
+                                         self.grp_start_host.ctypes.data, self.grp_csum_host.ctypes.data,
+                                         self.step_lo.ctypes.data, self.step_mid.ctypes.data,
                                          self.step_hi.ctypes.data, self.step_kind.ctypes.data, self.nsteps,
                                          self.max_multi, X.data_ptr(), int(m), ldx, sc.data_ptr(), sc.numel(),
                                          stream_ptr()), "rla_sptrsv_solve_f64")
