@@ -125,8 +125,14 @@ def run_c5(rank, world, dev, steps=10, warmup=3, hbm_peak=None, dmma_peak=None):
     kind = "srht" if "srht" in out else "gauss"
     t_all, l_all = timed(lambda: rangefinder.sketched_range_finder(U, n, K, 0, kind, rank, world, reducer=reducer),
                          max(2, steps // 2), 1)
+    # the reference's own variant of this step stops at the QR (gram_schmidt + T = pinv(R),
+    # mor/sketched_reductor.py:94-95); reported beside the full sketch + QR + SVD step
+    t_qr_only, _ = timed(lambda: rangefinder.sketched_range_finder(U, n, K, 0, kind, rank, world, reducer=reducer,
+                                                                   svd=False), max(2, steps // 2), 1)
     res.update(value=M * n * 8 / t_all / 1e6, unit="GB/s", ms_per_step=t_all, cols_per_s=M / t_all * 1e3,
-               gpu_launches=int(l_all), embedding=kind, phases=out)
+               gpu_launches=int(l_all), embedding=kind, phases=out,
+               qr_only={"ms_per_step": t_qr_only, "value": M * n * 8 / t_qr_only / 1e6, "unit": "GB/s",
+                        "what": "sketch + exchange + thin QR + T = R^-1 (no SVD)"})
     if reducer is not None:
         reducer.check_status()
         reducer.close()
