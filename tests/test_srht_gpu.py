@@ -116,3 +116,27 @@ def test_complex_input(rb):
 def test_bad_arguments(rb):
     with pytest.raises(AssertionError):
         rb.srht(np.zeros((2, 2, 2)), 3, seed=0)
+
+
+def test_warp_specialised_kernel_vs_oracle(rb, monkeypatch):
+    """Small problems take the single-role kernel by default; force the warp-specialised one
+    (the kernel the full-size blocks run on) and compare with the oracle: ragged last tile,
+    several passes (k > 4096 distinct indices), unaligned rows, float32."""
+    monkeypatch.setenv("RLA_SRHT_VARIANT", "0")
+    for m, n, k, seed in [(3, 2 ** 16 + 3, 4000, 7), (2, 2 ** 18, 9000, 8), (5, 2 ** 14, 100, 9), (1, 70000, 1, 10)]:
+        x = np.random.RandomState(200 + seed).standard_normal((m, n))
+        assert rel_fro(rb.srht(x, k, seed=seed), oracle.srht(x, k, seed=seed)) < TOL64
+    big = torch.randn(3, 2 ** 15 + 9, dtype=torch.float64, device="cuda")
+    xs = big[:, 1:2 ** 15 + 2]                     # odd offset: staged (scalar) tile loads
+    assert rel_fro(rb.srht(xs, 300, seed=4).cpu().numpy(), oracle.srht(xs.cpu().numpy(), 300, seed=4)) < TOL64
+    x32 = np.random.RandomState(11).standard_normal((3, 2 ** 16)).astype(np.float32)
+    assert rel_fro(rb.srht(x32, 500, seed=2), oracle.srht(x32.astype(np.float64), 500, seed=2)) < TOL32
+
+
+def test_warp_specialised_kernel_matches_single_role_kernel(rb, monkeypatch):
+    x = torch.randn(6, 2 ** 19, dtype=torch.float64, device="cuda")
+    monkeypatch.setenv("RLA_SRHT_VARIANT", "1")
+    y1 = rb.srht(x, 4000, seed=0)
+    monkeypatch.setenv("RLA_SRHT_VARIANT", "0")
+    y0 = rb.srht(x, 4000, seed=0)
+    assert float(torch.linalg.norm(y0 - y1) / torch.linalg.norm(y1)) < 1e-13
