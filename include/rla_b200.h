@@ -197,6 +197,10 @@ int rla_svd_jacobi_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
  * tests); falls back to the one-CTA kernel when the shape is out of range or ws is too small
  * (rla_gram_schmidt_workspace_bytes returns 0 when the grid kernel does not apply). */
 size_t rla_gram_schmidt_workspace_bytes(int64_t r, int64_t k);
+/* Byte offset, inside the workspace, of the int32 status word the grid kernel leaves behind
+ * (0 = ok, 1 = a wait on another CTA's flag timed out: the result is NOT usable); -1 when the
+ * one-CTA kernel runs for this shape.  Callers read it after the launch and raise. */
+int64_t rla_gram_schmidt_status_offset(int64_t r, int64_t k);
 int rla_gram_schmidt_ws_f64(double *a_dev, int64_t r, int64_t k, int64_t lda, int64_t offset,
                             double *R_dev, int32_t *flags_dev,
                             double atol, double rtol, double reiteration_threshold,

@@ -52,6 +52,7 @@ _SIGS = {
                                    POINTER(c_int), _vp]),
     "rla_residual_norm_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int64, _vp, _vp, _vp]),
     "rla_gram_schmidt_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "rla_gram_schmidt_status_offset": (c_int64, [c_int64, c_int64]),
     "rla_gram_schmidt_ws_f64": (c_int, [_vp, c_int64, c_int64, c_int64, c_int64, _vp, _vp, c_double, c_double, c_double,
                                         _vp, c_size_t, _vp]),
     "rla_svd_jacobi_block_rows": (c_int, [c_int64, c_int64, c_int]),

@@ -621,6 +621,14 @@ extern "C" size_t rla_gram_schmidt_workspace_bytes(int64_t r, int64_t k) {
     return gs_layout(c, r, k).total;
 }
 
+// byte offset of the int32 status word inside the workspace (0 = ok, 1 = a flag wait timed out);
+// -1 when the grid kernel does not apply to this shape (the one-CTA kernel has no waits)
+extern "C" int64_t rla_gram_schmidt_status_offset(int64_t r, int64_t k) {
+    const GsCfg c = gs_config(r, k);
+    if (!c.rpc || !coop_ok()) return -1;
+    return (int64_t)gs_layout(c, r, k).status;
+}
+
 extern "C" int rla_gram_schmidt_ws_f64(double *a, int64_t r, int64_t k, int64_t lda, int64_t offset, double *R,
                                        int32_t *flags, double atol, double rtol, double thr, void *ws, size_t ws_bytes,
                                        void *stream) {

@@ -262,32 +262,26 @@ extern "C" int rla_spmm_csr_f64(const int64_t *rowptr, const int32_t *col, const
     return RLA_OK;
 }
 
-extern "C" size_t rla_gemm_nn_workspace_bytes(int64_t m, int64_t k, int64_t n) {
-    if (m <= 0 || k <= 0 || n <= 0) return 0;
-    const size_t tr = (size_t)n * (size_t)(k + (k & 1)) * sizeof(double);
-    return tr + rla_gemm_workspace_bytes(m, n, k);
+namespace rla {
+int lincomb_launch(const double *v, int64_t m, int64_t k, int64_t ldv, const double *x, int64_t n, int64_t ldx,
+                   double *out, int64_t ldo, cudaStream_t st);
 }
 
-// out(m, n) = V(m, k) * Theta(k, n): Theta is transposed into scratch (n x k, k contiguous)
-// and the product runs on the same tensor-core kernel as the sketch itself.
+// kept for ABI stability: the tall-skinny kernel needs no scratch
+extern "C" size_t rla_gemm_nn_workspace_bytes(int64_t m, int64_t k, int64_t n) {
+    (void)m; (void)k; (void)n;
+    return 0;
+}
+
+// out(m, n) = V(m, k) * Theta(k, n) with m, k small and n long: csrc/lincomb.cu (Theta read once
+// per 128 rows of the result, no transposed copy)
 extern "C" int rla_gemm_nn_f64(const double *v, int64_t m, int64_t k, int64_t ldv, const double *theta, int64_t n,
                                int64_t ldt, double *out, int64_t ldo, void *ws, size_t ws_bytes, void *stream) {
+    (void)ws; (void)ws_bytes;
     RLA_REQUIRE(m >= 0 && k >= 1 && n >= 0 && ldv >= k && ldt >= n && ldo >= n, "rla_gemm_nn_f64: bad sizes");
     if (m == 0 || n == 0) return RLA_OK;
-    RLA_REQUIRE(v && theta && out && ws, "rla_gemm_nn_f64: null pointer");
-    const int64_t kp = k + (k & 1);
-    const size_t tr = (size_t)n * kp * sizeof(double);
-    if (ws_bytes < tr + rla_gemm_workspace_bytes(m, n, k))
-        return fail(RLA_ERR_WORKSPACE, "rla_gemm_nn_f64: workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
-    double *tt = static_cast<double *>(ws);
-    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((k + 31) / 32));
-    RLA_REQUIRE(grid.y <= 65535, "rla_gemm_nn_f64: k too large");
-    transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(theta, k, n, ldt, tt, kp);
-    count_launch();
-    RLA_CUDA_CHECK(cudaGetLastError());
-    return rla_gauss_apply_explicit_f64(tt, n, k, kp, v, m, ldv, out, ldo, static_cast<char *>(ws) + tr,
-                                        ws_bytes - tr, stream);
+    RLA_REQUIRE(v && theta && out, "rla_gemm_nn_f64: null pointer");
+    return lincomb_launch(v, m, k, ldv, theta, n, ldt, out, ldo, (cudaStream_t)stream);
 }
 
 extern "C" int rla_gram_schmidt_f64(double *a, int64_t r, int64_t k, int64_t lda, int64_t offset, double *R,

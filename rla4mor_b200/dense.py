@@ -28,7 +28,12 @@ def _rows(x):
 
 
 def _ld(x):
-    return max(x.stride(0), x.shape[1]) if x.shape[0] > 1 else x.shape[1]
+    """Leading dimension handed to the kernels.  A single row has no meaningful stride of its own
+    (torch reports anything for a size-1 dimension): use the stride when it can be one (a row of
+    a padded buffer, as `_tma_friendly` builds for odd n), else the row length."""
+    if x.shape[0] > 1:
+        return max(x.stride(0), x.shape[1])
+    return x.stride(0) if x.stride(0) >= x.shape[1] else x.shape[1]
 
 
 def _tma_friendly(x):

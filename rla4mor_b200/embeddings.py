@@ -124,7 +124,10 @@ class RandomEmbedding:
     # -- embeddings.py:69-100
     def get_matrix(self):
         if self._matrix is None:
-            self._matrix = self._compute_matrix()
+            if getattr(self, "_matrix_dev", None) is not None:
+                self._matrix = self._matrix_dev.cpu().numpy()        # host view of the device-built matrix
+            else:
+                self._matrix = self._compute_matrix()
         return self._matrix
 
     def get_random_matrix(self):
@@ -138,6 +141,8 @@ class RandomEmbedding:
             seed = np.random.randint(0, high=2 ** 32 - 1)
         self._seed = seed
         self.update()
+        if not isinstance(self, SrhtEmbedding):          # SrhtEmbedding.update() is a no-op (:145-146): cache survives
+            self._matrix_dev = None
 
     def update(self):                                    # embeddings.py:108-113
         if not (self._random_matrix is None):
@@ -146,10 +151,41 @@ class RandomEmbedding:
             self._matrix = self._compute_matrix()
 
     def as_range_array(self):                            # embeddings.py:115-117
-        return self.range.from_numpy(self.get_matrix().T)
+        return DeviceVectorArray(self.range, self.get_matrix_device().T.contiguous())
 
     def as_source_array(self):                           # embeddings.py:120-122
-        return self.source.from_numpy(self.get_matrix())
+        return DeviceVectorArray(self.source, self.get_matrix_device())
+
+    # -- device-resident forms of the explicit matrices (consumed by
+    #    preconditioners/preconditioned_reductor.py:107-119,185-194 and preconditioned_rom.py:66):
+    #    nothing goes through host NumPy; get_matrix() is the host view of the same tensor
+    def get_matrix_device(self):
+        """The U -> l2 matrix (k, n) as a CUDA tensor, built on the device: explicit SRHT rows
+        from the closed form, Theta from the kernel's generator (or the uploaded MT19937 draw),
+        Q^H applied by the device operator."""
+        if getattr(self, "_matrix_dev", None) is None:
+            if self._matrix is not None:                 # same cache as get_matrix (incl. the get_random_matrix quirk)
+                import scipy.sparse as sp
+                m = self._matrix.toarray() if sp.issparse(self._matrix) else self._matrix
+                self._matrix_dev = as_device_block(np.ascontiguousarray(m))
+            else:
+                self._matrix_dev = self._compute_matrix_device()
+        return self._matrix_dev
+
+    def _compute_matrix_device(self):
+        return self._adjoint_sqrt_product_device(self._compute_random_matrix_device())
+
+    def _compute_random_matrix_device(self):
+        import scipy.sparse as sp
+        m = self._compute_random_matrix()
+        return as_device_block(np.ascontiguousarray(m.toarray() if sp.issparse(m) else m))
+
+    def _adjoint_sqrt_product_device(self, rmat):
+        """Q^H applied to the rows of a (k, n_Q) CUDA matrix (embeddings.py:185,261): conj(Q^H conj(rows))."""
+        Q = self.sqrt_product
+        if isinstance(Q, IdentityOperator):
+            return rmat
+        return Q.apply_adjoint(DeviceVectorArray(Q.range, rmat.conj() if rmat.is_complex() else rmat)).data
 
     # -- pyMOR machinery the call sites rely on
     def with_(self, **kwargs):
@@ -243,6 +279,7 @@ class SrhtEmbedding(RandomEmbedding):
         self.range_id = range_id
         self.range = DeviceVectorSpace(self.compute_dim(), id=range_id)
         self._matrix = None
+        self._matrix_dev = None
         self._random_matrix = None
         self._plans = {}
         self._order_dev = None
@@ -311,6 +348,14 @@ class SrhtEmbedding(RandomEmbedding):
         plan = self._plan(torch.float64, v.device)
         if self._order_dev is None:
             self._order_dev = torch.from_numpy(np.argsort(plan.idx_host, kind="stable").astype(np.int32)).to(v.device)
+        if v.is_complex():
+            # the matrix is real: adjoint of the real and imaginary parts separately (the reference
+            # multiplies by get_matrix().T, which is complex-safe)
+            re = self.apply_adjoint(v.real.contiguous())
+            im = self.apply_adjoint(v.imag.contiguous())
+            if isinstance(self.sqrt_product, IdentityOperator):
+                return _wrap_result(kind, self.source, torch.complex(re, im))
+            raise TypeError("SrhtEmbedding.apply_adjoint: complex blocks need an identity sqrt_product")
         v = v.to(torch.float64).contiguous()
         m = v.shape[0]
         out = torch.empty((m, n), dtype=torch.float64, device=v.device)
@@ -332,6 +377,10 @@ class SrhtEmbedding(RandomEmbedding):
         _warning_once("Computing explicit SRHT matrix")
         return self._get_random_rows(np.arange(self.range.dim))
 
+    def _compute_random_matrix_device(self):
+        _warning_once("Computing explicit SRHT matrix")
+        return self._get_random_rows_device(np.arange(self.range.dim))
+
     def _rows_value(self):
         """|entry| of the explicit matrix exactly as the reference forms it:
         fl(fl(sqrt(n/k)) * fl(1 / fl(2**(d/2))))  (embeddings.py:207-208 with srht.py:36)."""
@@ -341,16 +390,27 @@ class SrhtEmbedding(RandomEmbedding):
         return float(np.sqrt(n / k) * (np.float64(1.0) / np.float64(2 ** (d / 2))))
 
     def _get_random_rows(self, indices):                                   # :195-209
+        return self._get_random_rows_device(indices).cpu().numpy()
+
+    def _get_random_rows_device(self, indices):
+        """Rows `indices` of sqrt(n/k) H[s, :n] diag(r) as a CUDA tensor (closed form, bit-identical
+        to the reference's one-hot -> fht_oop -> scale route)."""
         torch = require_cuda()
         n = self.sqrt_product.range.dim
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+        if idx.size and (idx.min() < -self.range.dim or idx.max() >= self.range.dim):
+            raise IndexError(f"row index out of range for an embedding of dimension {self.range.dim}")   # sampling[ind], :206
+        idx = np.where(idx < 0, idx + self.range.dim, idx)
         plan = self._plan(torch.float64, torch.device("cuda", torch.cuda.current_device()))
-        rows = torch.as_tensor(np.asarray(indices, dtype=np.int64), device=plan.device)
+        rows = torch.as_tensor(idx, device=plan.device)
         out = torch.empty((len(rows), n), dtype=torch.float64, device=plan.device)
+        if len(rows) == 0:
+            return out
         with torch.cuda.device(plan.device):
             check(lib().rla_srht_rows_f64(plan.signs_dev.data_ptr(), n, plan.idx_dev.data_ptr(), rows.data_ptr(),
                                           len(rows), self._rows_value(), out.data_ptr(), out.stride(0),
                                           stream_ptr()), "rla_srht_rows_f64")
-        return out.cpu().numpy()
+        return out
 
 
 class GaussianEmbedding(RandomEmbedding):
@@ -370,6 +430,7 @@ class GaussianEmbedding(RandomEmbedding):
         self.range_id = range_id
         self.range = DeviceVectorSpace(self.compute_dim(), id=range_id)
         self._matrix = None
+        self._matrix_dev = None
         self._theta_dev = None
         # the reference draws Theta eagerly (:230); on-the-fly modes never hold it
         self._random_matrix = self._compute_random_matrix() if self._rng_mode == "mt19937" else None
@@ -399,8 +460,14 @@ class GaussianEmbedding(RandomEmbedding):
                 return apply_streamed(self.apply, U, k, return_host=True)
             return apply_streamed_rng(self._seed, self._kind(), 1.0 / np.sqrt(k), k, U, return_host=True)
         qu, kind = self._apply_sqrt_product(U)
+        if qu.is_complex():                                                # Theta is real: sketch both parts in one pass
+            m = qu.shape[0]
+            y2 = self.apply(torch.cat([qu.real, qu.imag], dim=0).to(torch.float64).contiguous()) \
+                if isinstance(self.sqrt_product, IdentityOperator) else None
+            if y2 is None:
+                raise TypeError("GaussianEmbedding.apply: complex blocks need an identity sqrt_product")
+            return _wrap_result(kind, self.range, torch.complex(y2[:m], y2[m:]))
         if qu.dtype != torch.float64:
-            assert not qu.is_complex(), "complex blocks: sketch real and imaginary parts separately"
             qu = qu.to(torch.float64)
         if self._rng_mode == "mt19937":
             if self._theta_dev is None or self._theta_dev.device != qu.device:
@@ -417,8 +484,7 @@ class GaussianEmbedding(RandomEmbedding):
         if isinstance(U, DeviceVectorArray):
             assert U in self.range
         v, kind = _unwrap(U)
-        mat = torch.from_numpy(np.ascontiguousarray(self.get_matrix())).to(v.device)
-        return _wrap_result(kind, self.source, gemm_nn(v.to(torch.float64), mat))
+        return _wrap_result(kind, self.source, gemm_nn(v.to(torch.float64), self.get_matrix_device()))
 
     def _compute_matrix(self):                                             # :258-262
         gauss = self._random_matrix if self._random_matrix is not None else self._compute_random_matrix()
@@ -431,6 +497,19 @@ class GaussianEmbedding(RandomEmbedding):
         if self._rng_mode == "mt19937":
             return np.random.RandomState(seed).normal(size=(k, n), loc=0, scale=1 / np.sqrt(k))
         return dense.theta_materialize(seed, self._kind(), 1.0 / np.sqrt(k), k, n).cpu().numpy()
+
+    def _compute_random_matrix_device(self):
+        torch = require_cuda()
+        k = self.range.dim
+        n = self.sqrt_product.range.dim
+        if self._rng_mode == "mt19937":
+            # the reference's Theta is a host MT19937 draw (that is what makes it bit-identical);
+            # it is uploaded once and shared with apply()
+            if self._theta_dev is None:
+                gauss = self._random_matrix if self._random_matrix is not None else self._compute_random_matrix()
+                self._theta_dev = torch.from_numpy(gauss).cuda()
+            return self._theta_dev
+        return dense.theta_materialize(self._seed, self._kind(), 1.0 / np.sqrt(k), k, n)
 
 
 class IdentityEmbedding(RandomEmbedding):
@@ -448,6 +527,7 @@ class IdentityEmbedding(RandomEmbedding):
         self.range_id = range_id
         self.range = DeviceVectorSpace(self.compute_dim(), id=range_id)
         self._matrix = None
+        self._matrix_dev = None
         self._random_matrix = self._compute_random_matrix()
 
     def compute_dim(self):                                                 # :291-292
@@ -498,6 +578,7 @@ class EmbeddingVectorized(RandomEmbedding):
         self.range = embedding.range
         self.range_id = range_id
         self._matrix = None
+        self._matrix_dev = None
         self._random_matrix = None
 
     def compute_dim(self):                                                 # :337-350
@@ -540,6 +621,7 @@ class BlockGaussianEmbedding(RandomEmbedding):
         self.range_id = range_id
         self.range = DeviceVectorSpace(self.compute_dim(), id=range_id)
         self._matrix = None
+        self._matrix_dev = None
         self._random_matrix = None
         # block sizes (:393-400)
         max_block_size = options.get("max_block_size")
@@ -603,3 +685,19 @@ class BlockGaussianEmbedding(RandomEmbedding):
 
     def get_block(self, ind):                                              # :463-467
         return self._adjoint_sqrt_product(self._get_random_block(ind))
+
+    def _get_random_block_device(self, ind):
+        torch = require_cuda()
+        if self._rng_mode == "mt19937":
+            return torch.from_numpy(self._get_random_block(ind)).cuda()
+        k = self.range.dim
+        n = self.sqrt_product.range.dim
+        return dense.theta_materialize(int(self.block_seeds[ind]), self._kind(), 1.0 / np.sqrt(k), self.block_sizes[ind], n)
+
+    def get_block_device(self, ind):
+        """Block `ind` of the U -> l2 matrix as a CUDA tensor (preconditioned_reductor.py:185-194)."""
+        return self._adjoint_sqrt_product_device(self._get_random_block_device(ind))
+
+    def _compute_random_matrix_device(self):
+        import torch
+        return torch.cat([self._get_random_block_device(i) for i in range(self.n_blocks)], dim=0)

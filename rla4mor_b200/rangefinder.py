@@ -18,7 +18,7 @@ from . import reductor_ops as ops
 from . import sharding
 
 
-def sketch_block(U_local, n, k, seed, kind="srht", rank=0, world=1, group=None, reducer=None):
+def sketch_block(U_local, n, k, seed, kind="srht", rank=0, world=1, group=None, reducer=None, check=True):
     """(m, k) sketch of the block whose slab `U_local` (m, hi - lo) lives on this rank.
     `reducer` (peer.PeerSketchReducer): exchange the partials over NVLink peer memory
     (csrc/peer.cu) instead of an NCCL all-reduce."""
@@ -29,9 +29,9 @@ def sketch_block(U_local, n, k, seed, kind="srht", rank=0, world=1, group=None, 
         from . import dense
         return dense.embed_apply_rng(seed, 1 if kind == "rademacher" else 0, 1.0 / np.sqrt(k), k, U_local)
     if kind == "srht":
-        return sharding.srht_row_sharded(U_local, n, k, seed, rank, world, group, reducer)
+        return sharding.srht_row_sharded(U_local, n, k, seed, rank, world, group, reducer, check)
     return sharding.gaussian_row_sharded(U_local, n, k, seed, rank, world, 1 if kind == "rademacher" else 0, group,
-                                         reducer)
+                                         reducer, check)
 
 
 def thin_qr(S):
@@ -74,8 +74,10 @@ def sketch_svd(S, want_v=True, precondition=None, qr=None):
 
 def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, group=None, svd=True, reducer=None):
     """Returns dict(sketch, Q, R, T[, s, W]) -- all small (m x k, m x m) device tensors."""
-    S = sketch_block(U_local, n, k, seed, kind, rank, world, group, reducer)
+    S = sketch_block(U_local, n, k, seed, kind, rank, world, group, reducer, check=False)
     Q, R = thin_qr(S)
+    if reducer is not None and world > 1:
+        reducer.check_status()                          # thin_qr has synchronised already: this read is free
     out = {"sketch": S, "Q": Q, "R": R, "T": ops.pinv_R(R)}
     if svd:
         Urows, s, W = sketch_svd(S, want_v=True, qr=(Q, R))

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import dense
-from ._lib import check, lib, stream_ptr
+from ._lib import RlaError, check, lib, stream_ptr
 
 
 def _rows(x):
@@ -31,7 +31,9 @@ def spmm_csr(rowptr, col, val, shape, u):
 
 
 def gemm_nn(v, theta):
-    """(m, k) @ (k, n) -> (m, n): adjoint / basis update (mor/sketched_reductor.py:99-100)."""
+    """(m, k) @ (k, n) -> (m, n) with m, k small and n long: adjoints (V @ get_matrix()) and the
+    basis updates of mor/sketched_reductor.py:97-108 (csrc/lincomb.cu: theta read once per 128
+    rows of the result, result written once)."""
     v, theta = _rows(v).to(torch.float64), _rows(theta).to(torch.float64)
     m, k = v.shape
     assert theta.shape[0] == k
@@ -41,13 +43,17 @@ def gemm_nn(v, theta):
         return out
     if k == 0:
         return out.zero_()
-    v = dense._tma_friendly(v)
     with torch.cuda.device(v.device):
-        ws = dense._workspace(lib().rla_gemm_nn_workspace_bytes(m, k, n), v.device)
         check(lib().rla_gemm_nn_f64(v.data_ptr(), m, k, dense._ld(v), theta.data_ptr(), n, dense._ld(theta),
-                                    out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(), stream_ptr()),
+                                    out.data_ptr(), out.stride(0), None, 0, stream_ptr()),
               "rla_gemm_nn_f64")
     return out
+
+
+def lincomb(coefficients, rows):
+    """pyMOR `VectorArray.lincomb`: rows of the result = coefficients (r', r) @ rows (r, n)
+    (rb.lincomb(T.T), mor/sketched_reductor.py:99-100)."""
+    return gemm_nn(coefficients, rows)
 
 
 def gram(a, b):
@@ -73,8 +79,14 @@ def gram_schmidt(A, offset=0, atol=1e-13, rtol=1e-13, reiteration_threshold=9e-1
                                             float(atol), float(rtol), float(reiteration_threshold),
                                             ws.data_ptr(), ws.numel(), stream_ptr()),
               "rla_gram_schmidt_ws_f64")
+        soff = lib().rla_gram_schmidt_status_offset(r, k)
     keep = flags[:r] == 0
-    if not bool(keep.all()):
+    all_kept = bool(keep.all())                     # synchronises: the status word below is final
+    if soff >= 0 and soff + 4 <= ws.numel() and int(ws[soff:soff + 4].view(torch.int32).item()) != 0:
+        # a CTA gave up waiting for another CTA's flag (pre-emption, debugger, shared GPU):
+        # Q and R are only partly orthogonalised
+        raise RlaError("gram_schmidt: the grid-synchronised kernel timed out waiting on a flag; result discarded")
+    if not all_kept:
         A, R = A[keep], R[keep]
     return A, R
 
@@ -145,7 +157,6 @@ def svd_jacobi(S, want_v=False, max_sweeps=30, tol=None, block=True):
                                                  V.data_ptr() if want_v else None, _PAIRS[key].data_ptr(), B,
                                                  scratch.data_ptr(), int(max_sweeps), float(tol), stream_ptr()),
                   "rla_svd_jacobi_block_f64")
-        svd_jacobi.last_info = scratch[:3]              # {sweeps, converged, timeout} (device; read lazily)
     else:
         key = (m, A.device.index)
         if key not in _PAIRS:
@@ -158,6 +169,11 @@ def svd_jacobi(S, want_v=False, max_sweeps=30, tol=None, block=True):
                                            int(max_sweeps), float(tol), ctypes.byref(done), stream_ptr()),
                   "rla_svd_jacobi_f64")
     order = torch.argsort(s, descending=True)
+    if B:
+        info = scratch[:3].cpu()                    # {sweeps, converged, timeout}; the sort above follows the launch anyway
+        if int(info[2]) != 0:
+            raise RlaError("svd_jacobi: the block kernel timed out waiting on a block flag; result discarded")
+        svd_jacobi.last_info = info
     s = s[order]
     A = A[order]
     U_rows = A / torch.clamp(s, min=torch.finfo(torch.float64).tiny).unsqueeze(1)

@@ -81,7 +81,7 @@ def row_sharded_sketch(local_sketch, factor=None, group=None):
 
 
 # --------------------------------------------------------------------- device front ends
-def srht_row_sharded(x_slab, n, k, seed, rank, world, group=None, reducer=None):
+def srht_row_sharded(x_slab, n, k, seed, rank, world, group=None, reducer=None, check=True):
     """Row-sharded SRHT on the GPU: x_slab is this rank's (m, hi - lo) CUDA slab.
 
     With `reducer` (a peer.PeerSketchReducer for this (m, k)) the local kernel writes its
@@ -126,7 +126,10 @@ def srht_row_sharded(x_slab, n, k, seed, rank, world, group=None, reducer=None):
             plan.apply(x_slab, scale=scale, out=part)
         else:
             part.zero_()
-        return reducer.reduce(high=high)
+        out = reducer.reduce(high=high)
+        if check:
+            reducer.check_status()      # synchronises; pass check=False inside timed loops and check once afterwards
+        return out
     if hi <= lo:
         return all_reduce_sum(torch.zeros((m, k), dtype=x_slab.dtype, device=x_slab.device), group)
     return row_sharded_sketch(lambda: plan.apply(x_slab, scale=scale), factor, group)
@@ -135,7 +138,7 @@ def srht_row_sharded(x_slab, n, k, seed, rank, world, group=None, reducer=None):
 _SLAB_PLANS = {}
 
 
-def gaussian_row_sharded(x_slab, n, k, seed, rank, world, kind=0, group=None, reducer=None):
+def gaussian_row_sharded(x_slab, n, k, seed, rank, world, kind=0, group=None, reducer=None, check=True):
     """Row-sharded on-the-fly Gaussian / Rademacher sketch on the GPU (`reducer`: see srht_row_sharded)."""
     import torch
     from . import dense
@@ -149,7 +152,10 @@ def gaussian_row_sharded(x_slab, n, k, seed, rank, world, kind=0, group=None, re
             dense.embed_apply_rng(seed, kind, 1.0 / np.sqrt(k), k, x_slab, col0=lo, out=part)
         else:
             part.zero_()
-        return reducer.reduce()
+        out = reducer.reduce()
+        if check:
+            reducer.check_status()
+        return out
     if hi <= lo:
         return all_reduce_sum(torch.zeros((m, k), dtype=torch.float64, device=x_slab.device), group)
     assert x_slab.shape[1] == hi - lo

@@ -37,6 +37,9 @@ def apply_streamed(apply_fn, U_host, k, rows_per_chunk=None, out=None, device=No
     main = torch.cuda.current_stream(device)
     copy = torch.cuda.Stream(device)
     bufs = [torch.empty((rows_per_chunk, n), dtype=U_host.dtype, device=device) for _ in range(2)]
+    # the staging buffers come from the caching allocator of the MAIN stream and may be blocks whose
+    # last consumer is still running there: the first copies must not overtake that work
+    copy.wait_stream(main)
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     chunks = [(lo, min(lo + rows_per_chunk, m)) for lo in range(0, m, rows_per_chunk)]
@@ -82,6 +85,7 @@ def apply_streamed_rng(seed, kind, scale, k, U_host, cols_per_slab=None, device=
     main = torch.cuda.current_stream(device)
     copy = torch.cuda.Stream(device)
     bufs = [torch.empty((m, cols_per_slab), dtype=torch.float64, device=device) for _ in range(2)]
+    copy.wait_stream(main)                              # see apply_streamed
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     spitch = U_host.stride(0) * 8

@@ -150,6 +150,8 @@ class MatrixOperator:
         self.sparse = sp.issparse(matrix)
         if self.sparse:
             csr = matrix.tocsr()
+            if np.iscomplexobj(csr.data):
+                raise TypeError("MatrixOperator: complex sparse matrices are not supported (split real/imaginary parts)")
             csr.sort_indices()
             self.shape = csr.shape
             self.rowptr = torch.from_numpy(csr.indptr.astype(np.int64)).cuda()

@@ -79,7 +79,7 @@ def run_c5(rank, world, dev, steps=10, warmup=3, hbm_peak=None, dmma_peak=None):
     for kind in ("srht", "gauss"):
         if kind == "srht" and slab is None:
             continue
-        sk = lambda red=reducer: rangefinder.sketch_block(U, n, K, 0, kind, rank, world, reducer=red)
+        sk = lambda red=reducer: rangefinder.sketch_block(U, n, K, 0, kind, rank, world, reducer=red, check=False)
         S = sk()
         t_peer, l_peer = timed(sk)
         entry = {"sketch_ms": t_peer, "launches_per_step": int(l_peer)}
