@@ -133,6 +133,13 @@ int rla_dmma_peak_tflops(double *tflops, void *scratch_dev, void *stream);
 
 /* Theta materialised in device memory (drawn by the host exactly as
  * rla/embeddings.py:265-270 does). */
+/* Philox4x32-10 of Random123 (Salmon et al., SC'11), the generator behind the on-the-fly Theta:
+ * `count` items of 6 words {c0, c1, c2, c3, k0, k1} -> 4 output words each.  The host and the
+ * device form run the same source (csrc/rng.cuh); tests pin both to the published known-answer
+ * vectors. */
+int rla_philox4x32_10_host(const uint32_t *ctr_key, int64_t count, uint32_t *out);
+int rla_philox4x32_10_device(const uint32_t *ctr_key_dev, int64_t count, uint32_t *out_dev, void *stream);
+
 int rla_gauss_apply_explicit_f64(const double *theta_dev, int64_t k, int64_t n, int64_t ldt,
                                  const double *u_dev, int64_t m, int64_t ldu,
                                  double *y_dev, int64_t ldy,
@@ -142,7 +149,14 @@ int rla_gauss_apply_explicit_f64(const double *theta_dev, int64_t k, int64_t n, 
  * `seed`), never materialised: element (row0 + i, col0 + j) of the virtual
  * k_total x n_total matrix is scale * g(seed, row0 + i, col0 + j) with g a
  * standard normal (kind 0, Box-Muller) or a Rademacher +-1 (kind 1).
- * y[c, i] (+)= sum_j theta[row0 + i, col0 + j] * u[c, j]   for i < k_blk, j < n. */
+ * y[c, i] (+)= sum_j theta[row0 + i, col0 + j] * u[c, j]   for i < k_blk, j < n.
+ * Reproducibility: the Philox words are exact integer arithmetic (known-answer tested on host
+ * and device, rla_philox4x32_10_*), so kind 1 is the same on every device.  Kind 0 turns them
+ * into normals with FP32 Box-Muller on the SFU (MUFU lg2 / sin / cos approximations): the map
+ * (kind, seed, row, col) -> Theta is bit-stable on sm_100 -- rla_theta_materialize_f64 runs the
+ * same device function -- but another architecture may round the last FP32 bits differently.
+ * For a Theta that is identical everywhere use options['rng'] = 'mt19937' (host draw, explicit
+ * GEMM) or kind 1. */
 int rla_embed_apply_rng_f64(uint64_t seed, int kind, double scale,
                             int64_t row0, int64_t k_blk, int64_t col0, int64_t n,
                             const double *u_dev, int64_t m, int64_t ldu,

@@ -501,6 +501,33 @@ extern "C" int rla_dmma_peak_tflops(double *tflops, void *scratch_dev, void *str
     return RLA_OK;
 }
 
+namespace rla {
+__global__ void philox_kat_kernel(const uint32_t *__restrict__ in, int64_t count, uint32_t *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const PhiloxOut p = philox4x32_10(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3], in[6 * i + 4], in[6 * i + 5]);
+    out[4 * i] = p.x; out[4 * i + 1] = p.y; out[4 * i + 2] = p.z; out[4 * i + 3] = p.w;
+}
+}  // namespace rla
+
+extern "C" int rla_philox4x32_10_host(const uint32_t *in, int64_t count, uint32_t *out) {
+    RLA_REQUIRE(count >= 0 && (count == 0 || (in && out)), "rla_philox4x32_10_host: bad arguments");
+    for (int64_t i = 0; i < count; ++i) {
+        const PhiloxOut p = philox4x32_10(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3], in[6 * i + 4], in[6 * i + 5]);
+        out[4 * i] = p.x; out[4 * i + 1] = p.y; out[4 * i + 2] = p.z; out[4 * i + 3] = p.w;
+    }
+    return RLA_OK;
+}
+
+extern "C" int rla_philox4x32_10_device(const uint32_t *in, int64_t count, uint32_t *out, void *stream) {
+    RLA_REQUIRE(count >= 0 && (count == 0 || (in && out)), "rla_philox4x32_10_device: bad arguments");
+    if (count == 0) return RLA_OK;
+    philox_kat_kernel<<<(unsigned)((count + 127) / 128), 128, 0, (cudaStream_t)stream>>>(in, count, out);
+    count_launch();
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
+
 extern "C" size_t rla_gemm_workspace_bytes(int64_t m, int64_t k, int64_t n) {
     if (m <= 0 || k <= 0 || n <= 0) return 0;
     const GemmPlan p = plan_gemm(m, k, n);

@@ -658,15 +658,20 @@ class BlockGaussianEmbedding(RandomEmbedding):
         off = 0
         for i in range(len(self.block_sizes)):
             b = self.block_sizes[i]
-            out = result[:, off:off + b]
-            if self._rng_mode == "mt19937":
-                gauss = torch.from_numpy(self._get_random_block(i)).to(V.device)
-                out.copy_(dense.gauss_apply_explicit(gauss, V))
-            else:
-                # independent stream per block: the block's own seed, rows 0..b-1
-                out.copy_(dense.embed_apply_rng(int(self.block_seeds[i]), self._kind(), 1.0 / np.sqrt(k), b, V))
+            result[:, off:off + b].copy_(self._apply_block(i, V))
             off += b
         return _wrap_result(kind, self.range, result)
+
+    def _apply_block(self, i, V):
+        """(m, b_i) sketch of the CUDA block V (already Q U) by row block i of Theta (:430-432)."""
+        import torch
+        k = self.range.dim
+        b = self.block_sizes[i]
+        if self._rng_mode == "mt19937":
+            gauss = torch.from_numpy(self._get_random_block(i)).to(V.device)
+            return dense.gauss_apply_explicit(gauss, V)
+        # independent stream per block: the block's own seed, rows 0..b-1
+        return dense.embed_apply_rng(int(self.block_seeds[i]), self._kind(), 1.0 / np.sqrt(k), b, V)
 
     def _compute_matrix(self):                                             # :437-441
         return self._adjoint_sqrt_product(self._compute_random_matrix())

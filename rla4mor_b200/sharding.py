@@ -80,7 +80,89 @@ def row_sharded_sketch(local_sketch, factor=None, group=None):
     return all_reduce_sum(part, group)
 
 
+# ------------------------------------------------------------------ Theta-row-sharded (k split)
+def theta_row_shard(k, rank, world):
+    """Half-open range [lo, hi) of the SKETCH rows (rows of Theta) owned by `rank`: the
+    BlockGaussianEmbedding decomposition (rla/embeddings.py:393-400) spread over ranks.  Every rank
+    holds the whole block U; the sketch comes out split along k."""
+    return column_shard(k, rank, world)
+
+
+def block_shard(n_blocks, rank, world):
+    """Blocks of a BlockGaussianEmbedding owned by `rank` (contiguous, balanced)."""
+    lo, hi = column_shard(n_blocks, rank, world)
+    return list(range(lo, hi))
+
+
+def theta_row_sharded_sketch(local_sketch, k, rank, world, group=None, gather=True):
+    """local_sketch(lo, hi) -> this rank's (m, hi - lo) columns of the sketch (rows lo..hi of Theta
+    applied to the replicated block).  No reduction is needed -- the slices are disjoint; with
+    `gather` they are concatenated along k on every rank by ONE all-gather, else the local slice
+    and its range are returned."""
+    import torch
+    import torch.distributed as dist
+    lo, hi = theta_row_shard(k, rank, world)
+    part = local_sketch(lo, hi)
+    if not gather:
+        return part, (lo, hi)
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return part
+    m = part.shape[0]
+    width = -(-int(k) // int(world))                  # slices differ by at most one column: pad to the widest
+    buf = torch.zeros((m, width), dtype=part.dtype, device=part.device)
+    buf[:, :hi - lo] = part
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    cols = []
+    for g in range(world):
+        glo, ghi = theta_row_shard(k, g, world)
+        cols.append(parts[g][:, :ghi - glo])
+    return torch.cat(cols, dim=1)
+
+
 # --------------------------------------------------------------------- device front ends
+def gaussian_theta_row_sharded(x, k, seed, rank, world, kind=0, group=None, gather=True):
+    """Theta-row-sharded on-the-fly Gaussian / Rademacher sketch on the GPU: rank g generates and
+    applies rows [lo_g, hi_g) of the virtual k x n matrix (`row0` of rla_embed_apply_rng_f64) to the
+    replicated block x (m, n).  Equal to the single-GPU sketch column for column (same Philox
+    counters), bit for bit."""
+    from . import dense
+
+    def local(lo, hi):
+        return dense.embed_apply_rng(seed, kind, 1.0 / np.sqrt(k), hi - lo, x, row0=lo)
+    return theta_row_sharded_sketch(local, k, rank, world, group, gather)
+
+
+def block_gaussian_theta_row_sharded(embedding, U, rank, world, group=None, gather=True):
+    """BlockGaussianEmbedding.apply (rla/embeddings.py:425-434) with the row blocks of Theta dealt to
+    the ranks: each rank regenerates only its own blocks (per-block seeds, :402-407) and the
+    hstack of :433 becomes an all-gather.  U: replicated CUDA block (m, n)."""
+    import torch
+    import torch.distributed as dist
+    from .vectorarray import as_device_block
+    V = as_device_block(U).to(torch.float64)
+    mine = block_shard(embedding.n_blocks, rank, world)
+    offs = np.concatenate([[0], np.cumsum(embedding.block_sizes)])
+    cols = [embedding._apply_block(i, V) for i in mine]
+    part = torch.cat(cols, dim=1) if cols else torch.empty((V.shape[0], 0), dtype=torch.float64, device=V.device)
+    if not gather or not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return part if gather else (part, (int(offs[mine[0]]) if mine else 0, int(offs[mine[-1] + 1]) if mine else 0))
+    k = int(offs[-1])
+    width = max(int(offs[block_shard(embedding.n_blocks, g, world)[-1] + 1] - offs[block_shard(embedding.n_blocks, g, world)[0]])
+                if block_shard(embedding.n_blocks, g, world) else 0 for g in range(world))
+    buf = torch.zeros((V.shape[0], width), dtype=torch.float64, device=V.device)
+    buf[:, :part.shape[1]] = part
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    out = []
+    for g in range(world):
+        bl = block_shard(embedding.n_blocks, g, world)
+        w = int(offs[bl[-1] + 1] - offs[bl[0]]) if bl else 0
+        out.append(parts[g][:, :w])
+    res = torch.cat(out, dim=1)
+    assert res.shape[1] == k
+    return res
+
 def srht_row_sharded(x_slab, n, k, seed, rank, world, group=None, reducer=None, check=True):
     """Row-sharded SRHT on the GPU: x_slab is this rank's (m, hi - lo) CUDA slab.
 

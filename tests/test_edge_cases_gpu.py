@@ -94,3 +94,46 @@ def test_error_codes_from_the_abi(rb):
     with pytest.raises(RlaError):
         check(lib().rla_embed_apply_rng_f64(0, 0, 1.0, 0, 4, 8, 64, x.data_ptr(), 2, 64, y.data_ptr(), 8, 0,
                                             x.data_ptr(), 1 << 20, None), "col0 not multiple of 16")
+
+
+def test_single_vector_odd_n_on_the_fly_rng(rb):
+    """A (1, odd n) block on the in-kernel RNG path (advisor finding, round 1): the padded copy
+    must hand its real leading dimension to the TMA kernel; also through EmbeddingVectorized,
+    which always sketches one long vector."""
+    import torch
+    from rla4mor_b200 import dense
+    for n in (4097, 33, 1):
+        x = torch.randn(1, n, dtype=torch.float64, device="cuda")
+        for mode in ("philox", "philox_rademacher"):
+            g = rb.GaussianEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": 24, "rng": mode}, _seed=9)
+            y = g.apply(x)
+            theta = torch.from_numpy(g.get_random_matrix()).cuda()
+            ref = x @ theta.T
+            assert float(torch.linalg.norm(y - ref) / torch.linalg.norm(ref)) < 1e-12, (n, mode)
+    k1, nv = 7, 5                                   # vec(U) has 35 entries: odd
+    inner = rb.GaussianEmbedding(source=rb.DeviceVectorSpace(k1 * nv), options={"range_dim": 6, "rng": "philox"}, _seed=3)
+    vec = rb.EmbeddingVectorized(rb.DeviceVectorSpace(k1), nv, inner, options={})
+    W = torch.randn(nv, k1, dtype=torch.float64, device="cuda")
+    y = vec.apply(W)
+    ref = W.T.reshape(1, -1) @ torch.from_numpy(inner.get_random_matrix()).cuda().T
+    assert float(torch.linalg.norm(y - ref) / torch.linalg.norm(ref)) < 1e-12
+    b = rb.BlockGaussianEmbedding(source=rb.DeviceVectorSpace(35), options={"range_dim": 10, "max_block_size": 4, "rng": "philox"}, _seed=3)
+    yb = b.apply(W.T.reshape(1, -1))
+    refb = W.T.reshape(1, -1) @ torch.from_numpy(b.get_random_matrix()).cuda().T
+    assert float(torch.linalg.norm(yb - refb) / torch.linalg.norm(refb)) < 1e-12
+
+
+def test_theta_row_sharded_front_end_matches_single_gpu(rb):
+    """k split over (simulated) ranks: every rank's slice equals the corresponding columns of the
+    single-GPU sketch bit for bit (same Philox counters / same MT19937 blocks)."""
+    import torch
+    from rla4mor_b200 import dense, sharding
+    x = torch.randn(9, 3000, dtype=torch.float64, device="cuda")
+    k, seed, world = 50, 5, 4
+    full = dense.embed_apply_rng(seed, 0, 1.0 / np.sqrt(k), k, x)
+    got = torch.cat([sharding.gaussian_theta_row_sharded(x, k, seed, r, world, gather=False)[0] for r in range(world)], dim=1)
+    assert float(torch.linalg.norm(got - full) / torch.linalg.norm(full)) < 1e-14
+    emb = rb.BlockGaussianEmbedding(source=rb.DeviceVectorSpace(3000), options={"range_dim": 50, "max_block_size": 8}, _seed=11)
+    ref = emb.apply(x)
+    parts = [sharding.block_gaussian_theta_row_sharded(emb, x, r, world, gather=False)[0] for r in range(world)]
+    assert torch.equal(torch.cat(parts, dim=1), ref)

@@ -54,8 +54,25 @@ def _worker(rank, world, port, n, k, seed, out):
         if chi > clo:
             part[clo:chi] = torch.from_numpy(oracle.srht(x[clo:chi], k, seed=seed))
         yc = sharding.all_reduce_sum(part)
+        # --- Theta-row-sharded (k split): disjoint slices of the sketch, one all-gather, no reduction
+        yt = sharding.theta_row_sharded_sketch(lambda lo, hi: torch.from_numpy(x @ theta[lo:hi].T), k, rank, world)
+        sl, rng = sharding.theta_row_sharded_sketch(lambda lo, hi: torch.from_numpy(x @ theta[lo:hi].T), k, rank, world,
+                                                    gather=False)
+        assert rng == sharding.theta_row_shard(k, rank, world) and sl.shape == (3, rng[1] - rng[0])
+        # blocks of a BlockGaussianEmbedding dealt to the ranks (embeddings.py:393-407)
+        sizes = eo.block_sizes(k, 7)
+        seeds, _ = eo.block_seeds(seed, len(sizes))
+        mine = sharding.block_shard(len(sizes), rank, world)
+        cols = [x @ eo.block_gaussian_block(k, n, sizes[i], seeds[i]).T for i in mine]
+        width = max(sum(sizes[i] for i in sharding.block_shard(len(sizes), g, world)) for g in range(world))
+        buf = torch.zeros(3, width, dtype=torch.float64)
+        if cols:
+            c = np.hstack(cols); buf[:, :c.shape[1]] = torch.from_numpy(c)
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        yb = torch.cat([parts[g][:, :sum(sizes[i] for i in sharding.block_shard(len(sizes), g, world))] for g in range(world)], dim=1)
         if rank == 0:
-            np.savez(out, y=y.numpy(), yg=yg.numpy(), yc=yc.numpy())
+            np.savez(out, y=y.numpy(), yg=yg.numpy(), yc=yc.numpy(), yt=yt.numpy(), yb=yb.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -70,6 +87,10 @@ def _run(world, n, k, seed, tmp_path):
     assert np.linalg.norm(z["yc"] - ref) / np.linalg.norm(ref) == 0.0
     refg = eo.gaussian_apply(x, eo.gaussian_random_matrix(k, n, seed))
     assert np.linalg.norm(z["yg"] - refg) / np.linalg.norm(refg) < 1e-13
+    # k split: the same dot products (BLAS may block them differently on the host: rounding only)
+    assert np.linalg.norm(z["yt"] - refg) / np.linalg.norm(refg) < 1e-14
+    refb = eo.block_gaussian_apply(x, k, seed, 7)
+    assert np.linalg.norm(z["yb"] - refb) / np.linalg.norm(refb) < 1e-14
 
 
 def test_world2_pow2(tmp_path):
