@@ -17,6 +17,7 @@
 // cp.async (16 bytes per thread and request), V^T[kc.., rows] transposed on the way in.
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace rla {
 
@@ -131,10 +132,139 @@ lincomb_kernel(const double *__restrict__ v, int64_t ldv, const double *__restri
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-pipe version (default): the vector FP64 pipe of this part issues 32 DFMA lanes per
+// clock and SM, the DMMA path 64 (measured: tools/micro/fp64_dual_probe.cu, and the register-
+// tiled kernel above saturates at 19 TFLOP/s), so everything but tiny k is bound by the DFMA
+// rate unless it runs on mma.sync.m8n8k4.f64.
+//   out tile (WM*WTM) x (WN*32), 8 warps, warp tile WTM x 32 (WTM = 64 or 32);
+//   A fragment  a = V[i0 + g][k0 + t]   from the V chunk  [BM][16] (row stride 20 doubles)
+//   B fragment  b = X[k0 + t][j0 + g]   from the X chunk  [16][BN] (row stride BN + 4)
+//   D fragment  out[i0 + g][j0 + 2t .. +1]  -> one 16-byte store per lane
+// (g = lane / 4, t = lane % 4).  Row strides = 4 (mod 16) doubles make every fragment load one
+// conflict-free ld.shared.f64 per lane without any swizzle.  Chunks of 16 along k stream through
+// a 3-stage cp.async ring; rows / columns outside the problem are zero-filled by the copy
+// (src-size operand), so ragged m, k, n need no predicates in the math loop.
+constexpr int LM_BK = 16;
+constexpr int LM_STAGES = 3;
+constexpr int LM_LDV = LM_BK + 4;
+
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void lc_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int WTM, int WM>
+__global__ void __launch_bounds__(256, 1)
+lincomb_mma_kernel(const double *__restrict__ v, int64_t ldv, const double *__restrict__ x, int64_t ldx,
+                   double *__restrict__ out, int64_t ldo, int64_t m, int64_t k, int64_t n, int mtiles) {
+    constexpr int WN = 8 / WM, BM = WM * WTM, BN = WN * 32, LDX = BN + 4;
+    constexpr int MI = WTM / 8;                           // 8-row groups per warp tile
+    constexpr int XS = LM_BK * LDX, VS = BM * LM_LDV;     // doubles per stage
+    extern __shared__ __align__(16) unsigned char lm_smem[];
+    double *sx = reinterpret_cast<double *>(lm_smem);
+    double *sv = sx + LM_STAGES * XS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
+    const int64_t n0 = (int64_t)(blockIdx.x / mtiles) * BN;
+    const int64_t m0 = (int64_t)(blockIdx.x % mtiles) * BM;
+    const int nchunks = (int)((k + LM_BK - 1) / LM_BK);
+
+    auto load_stage = [&](int st, int c) {
+        const int64_t k0 = (int64_t)c * LM_BK;
+        double *dx = sx + st * XS, *dv = sv + st * VS;
+        // X chunk: 16 rows x BN/2 16-byte pieces
+        for (int id = tid; id < LM_BK * (BN / 2); id += 256) {
+            const int kk = id / (BN / 2), cc = (id % (BN / 2)) * 2;
+            const int64_t row = k0 + kk, col = n0 + cc;
+            const int bytes = (row < k && col < n) ? (col + 1 < n ? 16 : 8) : 0;
+            cp_async16_zfill(dx + kk * LDX + cc, bytes ? x + row * ldx + col : x, bytes);
+        }
+        // V chunk: BM rows x 8 pieces
+        for (int id = tid; id < BM * (LM_BK / 2); id += 256) {
+            const int r = id / (LM_BK / 2), cc = (id % (LM_BK / 2)) * 2;
+            const int64_t row = m0 + r, col = k0 + cc;
+            const int bytes = (row < m && col < k) ? (col + 1 < k ? 16 : 8) : 0;
+            cp_async16_zfill(dv + r * LM_LDV + cc, bytes ? v + row * ldv + col : v, bytes);
+        }
+    };
+
+    double acc[MI][4][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < LM_STAGES - 1; ++s) {
+        if (s < nchunks) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<LM_STAGES - 2>();
+        __syncthreads();                                  // chunk c has landed; everyone is done with chunk c - 1
+        if (c + LM_STAGES - 1 < nchunks) load_stage((c + LM_STAGES - 1) % LM_STAGES, c + LM_STAGES - 1);
+        cp_async_commit();
+        const double *px = sx + (c % LM_STAGES) * XS + wn * 32 + g;
+        const double *pv = sv + (c % LM_STAGES) * VS + (wm * WTM + g) * LM_LDV + t;
+#pragma unroll
+        for (int ks = 0; ks < LM_BK / 4; ++ks) {
+            double a[MI], b[4];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = pv[i * 8 * LM_LDV + ks * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = px[(ks * 4 + t) * LDX + j * 8];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) lc_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int64_t row = m0 + wm * WTM + 8 * i + g;
+        if (row >= m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t col = n0 + wn * 32 + 8 * j + 2 * t;
+            if (col + 1 < n) *reinterpret_cast<double2 *>(out + row * ldo + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+            else if (col < n) out[row * ldo + col] = acc[i][j][0];
+        }
+    }
+}
+
+template <int WTM, int WM>
+static int lincomb_mma_launch(const double *v, int64_t m, int64_t k, int64_t ldv, const double *x, int64_t n, int64_t ldx,
+                              double *out, int64_t ldo, cudaStream_t st) {
+    constexpr int WN = 8 / WM, BM = WM * WTM, BN = WN * 32;
+    const int64_t gx = (n + BN - 1) / BN, gy = (m + BM - 1) / BM;
+    RLA_REQUIRE(gx * gy < (int64_t(1) << 31), "lincomb: problem too large");
+    const int smem = (int)(LM_STAGES * (LM_BK * (BN + 4) + BM * LM_LDV) * sizeof(double));
+    auto kern = lincomb_mma_kernel<WTM, WM>;
+    RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)(gx * gy), 256, smem, st>>>(v, ldv, x, ldx, out, ldo, m, k, n, (int)gy);
+    count_launch();
+    RLA_CUDA_CHECK(cudaGetLastError());
+    return RLA_OK;
+}
+
 int lincomb_launch(const double *v, int64_t m, int64_t k, int64_t ldv, const double *x, int64_t n, int64_t ldx,
                    double *out, int64_t ldo, cudaStream_t st) {
     const int vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ldx % 2 == 0) &&
                        (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (ldo % 2 == 0);
+    const bool v_ok = (reinterpret_cast<uintptr_t>(v) % 16 == 0) && (ldv % 2 == 0);
+    static int force_fma = -1;
+    if (force_fma < 0) { const char *e = getenv("RLA_LINCOMB_FMA"); force_fma = e ? atoi(e) : 0; }
+    if (vec_ok && v_ok && !force_fma) {
+        // tensor pipe: 128 x 128 tiles for tall coefficient blocks, 64 x 256 / 32 x 256 below
+        if (m > 64) return lincomb_mma_launch<64, 2>(v, m, k, ldv, x, n, ldx, out, ldo, st);
+        if (m > 32) return lincomb_mma_launch<64, 1>(v, m, k, ldv, x, n, ldx, out, ldo, st);
+        return lincomb_mma_launch<32, 1>(v, m, k, ldv, x, n, ldx, out, ldo, st);
+    }
     const int64_t gx = (n + LC_BN - 1) / LC_BN;
     // rows per thread: the smallest tile that covers m in one pass, 128 rows per pass beyond
     const int tr = m <= 32 ? 2 : (m <= 64 ? 4 : 8);
