@@ -11,7 +11,11 @@ A step is one pass of the hot path over one block of synthetic vectors.  Workloa
                         generated on the fly (configs[1]; FP64 tensor-pipe bound)
     srht_c3             SRHT k=4000 on a float64 2^24 x 1024 block, column-sharded
                         (configs[2]; HBM bound); run as the `secondary` result
-    srht_c1             SRHT k=1000 on 2^16 x 200 (configs[0], the reference's CPU case)
+    srht_c1             SRHT k=1000 on 2^16 x 200 (configs[0], the one case the reference runs in
+                        full on the CPU: the oracle's whole srht() is timed beside it, L2 flushed
+                        between steps because the 105 MB block fits the 126 MB L2); `secondary`
+    sketched_reductor_c4  SketchedReductor.extend_basis on an n = 1e6, Q = 4 FEM-like problem with the
+                        LU inverse product (configs[3]; tools/bench_c4.py); `secondary`, rank 0
     rangefinder_c5      sketch + thin QR / SVD of a 2^23 x 256 block, k=1024, ROW-sharded with one
                         exchange of the (m, k) partials over NVLink peer memory (configs[4]);
                         second `secondary` result (tools/bench_c5.py)
@@ -38,6 +42,24 @@ WORKLOADS = {
     "srht_c3": dict(kind="srht", m=1024, logn=24, k=4000, config="configs[2]"),
     "srht_c1": dict(kind="srht", m=200, logn=16, k=1000, config="configs[0]"),
 }
+
+
+def workload_config(name, world, m_loc=None, note=None):
+    """The `config` object of the JSON line -- built by BOTH arms from the same inputs."""
+    wl = WORKLOADS[name]
+    n = 2 ** wl["logn"]
+    strong = name == "srht_c3"
+    if m_loc is None:
+        m_loc = wl["m"] // world if strong else wl["m"]
+    m_total = m_loc * world
+    cfg = {"workload": name, "baseline_config": wl["config"], "embedding": wl["kind"], "m_total": m_total,
+           "m_per_gpu": m_loc, "n": n, "k": wl["k"], "partition": f"columns x{world} (no collective)",
+           "scaling": "strong" if strong else "weak",
+           "l2": ("inputs larger than L2 (per-GPU block %.1f GB >> 126 MB)" % (m_loc * n * 8 / 1e9)) if m_loc * n * 8 > 2e8
+           else "L2 flushed between timed steps (256 MB write); per-step CUDA events"}
+    if note:
+        cfg["note"] = note
+    return cfg
 
 
 def parse():
@@ -150,16 +172,31 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1, which would leave the CPU arm's BLAS on one core: lift the
+    limit of every thread pool in the process to the host's core count."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    return cores
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU algorithm for the same workload on the host
     cores of this box (oracle port: /root/reference is a Python tree that does not travel
-    to the GPU box, so its restatement under oracle/ is what runs here)."""
+    to the GPU box, so its restatement under oracle/ -- checked against outputs of the executed
+    reference, tests/test_reference_goldens_cpu.py -- is what runs here)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = all_host_threads()
     wl = WORKLOADS[args.workload]
     m, n, k = wl["m"], 2 ** wl["logn"], wl["k"]
-    cores = os.cpu_count() or 1
+    extrapolated = True
     if wl["kind"] == "gauss":
         kb = 50
         U = host_block(m, n)
@@ -172,9 +209,12 @@ def run_reference(args):
         ms = min(m, 8 if wl["logn"] >= 22 else m)
         U = host_block(ms, n)
         step = lambda: cpu_srht_sample(U, k)
-        sample = f"{ms} of {m} vectors per step (srht() incl. its per-call sign/index draw); rate scaled per vector"
+        extrapolated = ms < m
+        sample = (f"{ms} of {m} vectors per step (srht() incl. its per-call sign/index draw); rate scaled per vector"
+                  if extrapolated else f"the whole {m} x 2^{wl['logn']} block per step (srht() incl. its sign/index draw)")
         scale = m / ms
-        threads = cores
+        import oracle.srht_oracle as so
+        threads = so.oracle_threads()
     for _ in range(max(1, min(args.warmup, 1))):
         step()
     t = []
@@ -183,16 +223,18 @@ def run_reference(args):
         t.append(dt)
         if sum(t) > 240:
             break
-    full = float(np.mean(t)) * scale                      # seconds for the whole block
+    full = float(np.mean(t)) * scale                      # seconds for one whole block
     gbs = m * n * 8 / full / 1e9
     line = {
         "impl": "reference", "metric": "sketch throughput", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": len(t), "warmup": min(args.warmup, 1), "ms_per_step": float(np.mean(t)) * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "baseline_config": wl["config"], "m": m, "n": n, "k": k,
-                   "cols_per_s": m / full, "extrapolated": True},
+        "higher_is_better": True, "scaling": "strong" if args.workload == "srht_c3" else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, max(1, args.gpus)),
+        "cols_per_s": m / full,
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
-                         "host_cpus": cores},
+                         "host_cpus": cores, "extrapolated": extrapolated,
+                         "note": "one host processes one block at this rate whatever N is (the GPU arm's weak-scaled "
+                                 "value is N blocks)"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,22 +284,42 @@ def run_ours(args):
             return float(t.item())
         return x
 
-    def timed(step, steps, warmup):
+    flush_buf = []
+
+    def timed(step, steps, warmup, flush=False):
+        """K timed steps.  Default: back to back, start-to-end CUDA events.  flush=True (inputs that
+        fit the 126 MB L2): a 256 MB buffer is overwritten before every step and each step is
+        timed by its own event pair (the flush is outside the timed region)."""
+        if flush and not flush_buf:
+            flush_buf.append(torch.empty(256 << 20, dtype=torch.uint8, device=dev))
         for _ in range(warmup):
+            if flush and flush_buf:
+                flush_buf[0].add_(1)
             step()
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         l0 = lib.rla_launch_count()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        evs[0].record()
-        for i in range(steps):
-            step()
-            evs[i + 1].record()
-        torch.cuda.synchronize()
-        ms = evs[0].elapsed_time(evs[-1])                    # the K timed steps, start to end
-        timed.last_step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        if flush:
+            pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for e0, e1 in pairs:
+                flush_buf[0].add_(1)
+                e0.record()
+                step()
+                e1.record()
+            torch.cuda.synchronize()
+            timed.last_step_ms = [e0.elapsed_time(e1) for e0, e1 in pairs]
+            ms = float(sum(timed.last_step_ms))
+        else:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            evs[0].record()
+            for i in range(steps):
+                step()
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            ms = evs[0].elapsed_time(evs[-1])                    # the K timed steps, start to end
+            timed.last_step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
         launches = lib.rla_launch_count() - l0
         clocks = sampler.stop() if rank == 0 else None
         barrier()
@@ -311,30 +373,34 @@ def run_ours(args):
             work = float(m_loc * n * 8 + m_loc * k * 8 + n + 4 * k)   # algorithmic bytes per rank per step
             roof = dict(bound="hbm", unit="GB/s", peak=float(peaks["hbm_gbs"]), peak_source=peak_src,
                         algorithmic="m*n*8 (read U once) + m*k*8 (write sketch) + n (signs) + 4k (indices) bytes per launch")
-        ms, launches, clocks = timed(step, steps, warmup)
+        small = m_loc * n * 8 < 2e8                          # fits L2: flush between steps
+        ms, launches, clocks = timed(step, steps, warmup, flush=small)
         t_step = ms / steps / 1e3
         achieved = work / t_step / (1e12 if roof["bound"] == "tensor" else 1e9)
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
-            traffic = (json.load(open(tpath)).get(name) or {}).get("bytes")
+            tj = json.load(open(tpath)).get(name) or {}
+            traffic = tj.get("bytes")
+            traffic_src = "not measured in this run: dram__bytes_read+write of the ncu --set full capture " + str(tj.get("source", "under profiles/"))
         best = min(timed.last_step_ms) / 1e3
-        roof.update(achieved=achieved, frac=achieved / roof["peak"], traffic=traffic,
+        roof.update(achieved=achieved, frac=achieved / roof["peak"], traffic=traffic, traffic_source=traffic_src,
+                    frac_best_step=work / best / (1e12 if roof["bound"] == "tensor" else 1e9) / roof["peak"],
                     achieved_best_step=work / best / (1e12 if roof["bound"] == "tensor" else 1e9),
                     step_ms=[round(v, 3) for v in timed.last_step_ms],
-                    kernel="sketch_gemm_kernel" if wl["kind"] == "gauss" else "srht_ws_kernel",
+                    kernel="sketch_gemm_kernel" if wl["kind"] == "gauss" else
+                    ("srht_ws_kernel" if m_loc * (n // 4096) >= 16384 else "srht_main_kernel"),
                     note="duration = whole step (main kernel + its small reduce/finalize kernel), CUDA events")
         res = {
             "workload": name, "value": m_total * n * 8 / t_step / 1e9, "unit": "GB/s",
             "cols_per_s": m_total / t_step, "ms_per_step": ms / steps, "gpu_launches": launches,
             "roofline": roof, "clocks": clocks,
-            "config": {"workload": name, "baseline_config": wl["config"], "embedding": wl["kind"], "m_total": m_total,
-                       "m_per_gpu": m_loc, "n": n, "k": k, "partition": f"columns x{world} (no collective)",
-                       "scaling": "strong" if strong else "weak",
-                       "l2": "inputs larger than L2 (per-GPU block %.1f GB >> 126 MB)" % (m_loc * n * 8 / 1e9)},
+            "config": workload_config(name, world, m_loc, note),
         }
-        if note:
-            res["config"]["note"] = note
+        if wl["kind"] == "srht" and clocks:
+            roof["note_power"] = ("frac is the mean over the back-to-back steps; frac_best_step the fastest step. A pure HBM "
+                                  "read stream already holds this board at its 1000 W cap (SM clock ~1.6 GHz, "
+                                  "profiles/srht_r02_experiments.txt); the 13 FP64 adds per element then run at that clock")
         # ---- end to end: host (pinned) block -> H2D -> sketch -> D2H of the result, per step
         if with_e2e:
             m_e = min(m_loc, max(1, (20 << 30) // (n * 8)))           # at most ~20 GiB of pinned memory
@@ -344,14 +410,26 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 e_step = lambda: apply_fn(host)                       # host block in, host sketch out
                 e_steps = max(2, min(steps, 5))
-                ems, _, _ = timed(e_step, e_steps, 1)
+                ems, _, _ = timed(e_step, e_steps, 1, flush=small)
                 te = ems / e_steps / 1e3
                 res["e2e"] = {"value": m_e * world * n * 8 / te / 1e9, "unit": "GB/s",
                               "h2d_bytes_per_step": int(m_e * n * 8), "d2h_bytes_per_step": int(m_e * k * 8),
                               "api": f"{type(emb).__name__}.apply(pinned host block) -> pinned host sketch; ~1 GiB pieces "
                                      "copied on a side stream under the sketch of the previous piece (streaming.py)",
                               "m_per_gpu": m_e, "ms_per_step": ems / e_steps, "cols_per_s": m_e * world / te}
-                if rank == 0 and with_cpu:
+                if rank == 0 and with_cpu and name == "srht_c1":
+                    # configs[0] is the one case the CPU reference runs in full: time it, no extrapolation
+                    import oracle.srht_oracle as so
+                    all_host_threads()
+                    cpu_srht_sample(host.numpy()[:1, :4096].copy(), 16)
+                    dts = [cpu_srht_sample(host.numpy(), k)[0] for _ in range(3)]
+                    dt = float(np.median(dts))
+                    res["cpu_baseline"] = {"value": m_e * n * 8 / dt / 1e9, "unit": "GB/s", "cores": so.oracle_threads(),
+                                           "kind": "port", "host_cpus": os.cpu_count(), "extrapolated": False,
+                                           "sample": f"the whole {m_e} x 2^{wl['logn']} block, oracle srht() incl. its sign/index "
+                                                     f"draw, median of 3: {dt * 1e3:.0f} ms", "cols_per_s": m_e / dt}
+                    del host
+                elif rank == 0 and with_cpu:
                     res["_host_block"] = host.numpy()
                 else:
                     del host
@@ -365,10 +443,14 @@ def run_ours(args):
     if not args.no_secondary and args.workload == "gauss_c2":
         # configs[2] first: the 137 GB block needs the whole HBM, and every workload is then timed
         # from an idle GPU (the FP64 GEMM leaves the board at its power cap for seconds)
-        secondary.append(run_workload("srht_c3", False, False, max(3, min(args.steps, 10)), max(3, args.warmup)))
+        secondary.append(run_workload("srht_c3", not args.no_e2e, False, max(3, min(args.steps, 10)), max(3, args.warmup)))
         secondary[-1].pop("_host_block", None)
         secondary[-1]["order"] = "timed before the primary workload"
         time.sleep(1.0)
+        # configs[0]: the reference's own CPU-sized case, with e2e and the whole CPU srht() beside it
+        secondary.append(run_workload("srht_c1", not args.no_e2e, not args.no_cpu_baseline and args.gpus == 1,
+                                      max(5, min(args.steps, 20)), max(3, args.warmup)))
+        secondary[-1].pop("_host_block", None)
     primary = run_workload(args.workload, not args.no_e2e, not args.no_cpu_baseline, args.steps, args.warmup)
     host_block_np = primary.pop("_host_block", None)
 
@@ -381,6 +463,14 @@ def run_ours(args):
                                     hbm_peak=float(peaks["hbm_gbs"]), dmma_peak=pk))
         except Exception as exc:                                       # never lose the primary line to a secondary
             secondary.append({"workload": "rangefinder_c5", "error": f"{type(exc).__name__}: {exc}"[:300]})
+        # configs[3]: SketchedReductor with the LU inverse product (rank 0; the other ranks wait at the barrier)
+        if rank == 0:
+            try:
+                from tools.bench_c4 import run_c4
+                secondary.append(run_c4(hbm_peak=float(peaks["hbm_gbs"]), with_cpu=not args.no_cpu_baseline and args.gpus == 1))
+            except Exception as exc:
+                secondary.append({"workload": "sketched_reductor_c4", "error": f"{type(exc).__name__}: {exc}"[:300]})
+        barrier()
 
     cpu = None
     if rank == 0 and world >= 1 and not args.no_cpu_baseline and args.gpus == 1:
@@ -415,7 +505,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": primary["config"], "cols_per_s": primary["cols_per_s"],
             "clocks": primary["clocks"], "e2e": primary.get("e2e"), "gpu_launches": primary["gpu_launches"],
             "roofline": primary["roofline"], "cpu_baseline": cpu,
-            "secondary": [{kk: vv for kk, vv in s.items() if kk != "e2e"} for s in secondary],
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

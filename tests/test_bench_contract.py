@@ -41,7 +41,21 @@ def test_reference_arm_json_line(monkeypatch, capsys):
         assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
         assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert line["config"]["workload"] == name
+        # the config object is the one our arm prints for the same workload and N (driver: same_config)
+        assert line["config"] == bench.workload_config(name, 1)
+        assert set(line["config"]) >= {"workload", "baseline_config", "embedding", "m_total", "m_per_gpu", "n", "k",
+                                        "partition", "scaling", "l2"}
     # ranks other than 0 print nothing
     monkeypatch.setenv("RANK", "1")
     bench.run_reference(bench.parse())
     assert capsys.readouterr().out == ""
+
+
+def test_reference_arm_lifts_the_thread_limit_torchrun_sets(monkeypatch):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core."""
+    bench = _load_bench()
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    cores = bench.all_host_threads()
+    assert cores == (os.cpu_count() or 1) and os.environ["OMP_NUM_THREADS"] == str(cores)
+    if cores > 1:
+        assert bench.blas_threads() > 1

@@ -15,7 +15,9 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 import rla4mor_b200 as rb
 from rla4mor_b200.factorization import InverseLuOperator
 
@@ -39,12 +41,15 @@ def fem_terms(nx, Q=4):
     return terms, (L + sp.eye(n)).tocsc(), n
 
 
-def main():
-    nx = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-    m = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    k = 1000
+def run_c4(nx=1000, m=64, k=1000, hbm_peak=6549.8, with_cpu=True):
+    """One dict for bench.py's `secondary` list (and for `python tools/bench_c4.py`)."""
     terms, R, n = fem_terms(nx)
-    res = {"workload": "sketched_reductor_c4", "n": n, "Q": len(terms), "m": m, "k": k}
+    lib = rb.lib()
+    res = {"workload": "sketched_reductor_c4", "unit": "ms",
+           "config": {"workload": "sketched_reductor_c4", "baseline_config": "configs[3]", "n": n, "Q": len(terms), "m": m,
+                      "k": k, "problem": f"P1-like 5-point FEM blocks on a {nx} x {nx} grid (SciPy-assembled; pyMOR is not in the image), "
+                                         "inner product R = L + I factored by SuperLU on the host as in the reference",
+                      "l2": "working set >> L2 (U block 0.5 GB, factors 0.9 GB)"}}
     space = rb.DeviceVectorSpace(n, id="S")
     ops_dev = [rb.MatrixOperator(A, source_id="S", range_id="S") for A in terms]
     t0 = time.time()
@@ -57,8 +62,12 @@ def main():
     U = torch.randn(m, n, dtype=torch.float64, device="cuda")
     Uva = space.from_numpy(U)
     res["spmm_ms"] = timeit(lambda: ops_dev[0].apply(Uva))
+    nnz_a = terms[0].nnz
+    res["spmm_algorithmic_GBs"] = (nnz_a * 12 + 2 * n * m * 8) / res["spmm_ms"] / 1e6
     V1 = ops_dev[0].apply(Uva)
+    l0 = lib.rla_launch_count()
     res["lu_solve_ms"] = timeit(lambda: rinv.apply(V1))
+    res["lu_solve_launches"] = int((lib.rla_launch_count() - l0) // 4)
     ldx = m + (m & 1)
     X = torch.randn(n, ldx, dtype=torch.float64, device="cuda")
     res["L_solve_ms"] = timeit(lambda: fL.solve_inplace(X.clone(), m))
@@ -66,15 +75,20 @@ def main():
     res["clone_ms"] = timeit(lambda: X.clone())
     # algorithmic traffic of one solve: every off-diagonal entry reads 8*m bytes of X and 12 bytes of the factor
     byts = (fL.nnz + fU.nnz) * (8 * m + 12) + 4 * n * m * 8
-    res["lu_solve_algorithmic_GBs"] = byts / res["lu_solve_ms"] / 1e6
+    res["roofline"] = {"bound": "hbm", "kernel": "sptrsv kernels (one LU solve of m right-hand sides)", "unit": "GB/s",
+                       "achieved": byts / res["lu_solve_ms"] / 1e6, "peak": hbm_peak,
+                       "frac": byts / res["lu_solve_ms"] / 1e6 / hbm_peak, "traffic": None,
+                       "algorithmic": "(nnz(L) + nnz(U)) * (8 m + 12) + 4 n m 8 bytes per solve"}
     # parity against SuperLU on a few right-hand sides, and the CPU time of the reference's call
     sub = min(m, 8)
     Vh = V1.data[:sub].cpu().numpy()
     t0 = time.time(); ref = rinv.factorization.solve(Vh.T).T; cpu_s = time.time() - t0
     got = rinv.apply(space.from_numpy(V1.data[:sub])).to_numpy()
     res["parity_rel_fro_vs_superlu"] = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
-    res["cpu_superlu_solve_s"] = {"rhs": sub, "seconds": cpu_s, "extrapolated_to_m_s": cpu_s * m / sub,
-                                  "host_cpus": os.cpu_count()}
+    if with_cpu:
+        res["cpu_baseline"] = {"value": cpu_s * m / sub * 1e3, "unit": "ms per 64-rhs LU solve", "cores": 1, "kind": "reference",
+                               "sample": f"SciPy SuperLU solve (what InverseLuOperator.apply calls, utilities/factorization.py:118-124) "
+                                         f"of {sub} right-hand sides: {cpu_s:.2f} s; scaled to {m}", "host_cpus": os.cpu_count()}
     for kind, opt in (("srht", {"range_dim": k}), ("gauss", {"range_dim": k, "rng": "philox"})):
         emb = (rb.SrhtEmbedding if kind == "srht" else rb.GaussianEmbedding)(source=space, options=opt, _seed=0)
         res[f"sketch_{kind}_ms"] = timeit(lambda: emb.apply(U))
@@ -84,8 +98,27 @@ def main():
                                           inverse_product=inv)
                 red.extend_basis(U)
                 return red
+            l0 = lib.rla_launch_count()
             res[f"extend_basis_{kind}_{name}_ms"] = timeit(ext, 2)
-    print(json.dumps(res))
+            res[f"extend_basis_{kind}_{name}_launches"] = int((lib.rla_launch_count() - l0) // 3)
+    # the headline of this config: one extend_basis(U) of m vectors with the SRHT and the LU inverse product
+    res["value"] = res["extend_basis_srht_lu_inverse_product_ms"]
+    res["ms_per_step"] = res["value"]
+    res["gpu_launches"] = res["extend_basis_srht_lu_inverse_product_launches"]
+    # the full-space basis update rb.lincomb(T.T) (mor/sketched_reductor.py:99-100) at this size
+    C = torch.randn(m, m, dtype=torch.float64, device="cuda")
+    from rla4mor_b200 import reductor_ops as rops
+    res["lincomb_ms"] = timeit(lambda: rops.lincomb(C, U))
+    res["lincomb_GBs"] = 2 * m * n * 8 / res["lincomb_ms"] / 1e6
+    del U, X, V1
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    nx = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    m = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    print(json.dumps(run_c4(nx, m)))
 
 
 if __name__ == "__main__":

@@ -133,6 +133,27 @@ def run_c5(rank, world, dev, steps=10, warmup=3, hbm_peak=None, dmma_peak=None):
                gpu_launches=int(l_all), embedding=kind, phases=out,
                qr_only={"ms_per_step": t_qr_only, "value": M * n * 8 / t_qr_only / 1e6, "unit": "GB/s",
                         "what": "sketch + exchange + thin QR + T = R^-1 (no SVD)"})
+    if world > 1 and slab is not None:
+        # parity of the row-sharded path against the CPU oracle on a small block (the 2-GPU pytest is
+        # skipped on 1-GPU boxes): the oracle is used as the CHECKER only, outside every timed region
+        try:
+            import oracle
+            from rla4mor_b200.peer import PeerSketchReducer
+            ms_, ns_, ks_ = 4, 2 ** 14 + 40, 96
+            xs = np.random.RandomState(99).standard_normal((ms_, ns_))
+            _, rg = sharding.srht_slabs(ns_, world)
+            a, b = rg[rank]
+            xloc = torch.from_numpy(np.ascontiguousarray(xs[:, a:b])).to(dev)
+            with PeerSketchReducer(ms_, ks_) as red_s:
+                ys = sharding.srht_row_sharded(xloc, ns_, ks_, 5, rank, world, reducer=red_s).cpu().numpy()
+            yn = sharding.srht_row_sharded(xloc, ns_, ks_, 5, rank, world).cpu().numpy()
+            ref = oracle.srht(xs, ks_, seed=5)
+            res["row_sharded_vs_oracle_rel"] = {
+                "peer_exchange": float(np.linalg.norm(ys - ref) / np.linalg.norm(ref)),
+                "nccl_allreduce": float(np.linalg.norm(yn - ref) / np.linalg.norm(ref)),
+                "case": f"SRHT, {ms_} x {ns_} (ragged), k={ks_}, seed 5, {world} slabs; tolerance 1e-12"}
+        except Exception as exc:
+            res["row_sharded_vs_oracle_rel"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     if reducer is not None:
         reducer.check_status()
         reducer.close()
