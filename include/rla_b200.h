@@ -254,22 +254,26 @@ int rla_residual_norm_f64(const double *S_dev, int64_t Q, int64_t k, int64_t r,
  * external column indices replaced by positions -- the strictly triangular part re-packed as CSR
  * (rowptr2 n + 1, col2 / val2 up to nnz, entries of a row sorted by column), the diagonal (1.0
  * where absent) and split; the solve therefore works on X in schedule order (X[p] = row
- * order_out[p], which rla_sptrsv_transpose_in/out produce with perm = pos[perm_r] etc.); the GROUPS (group g = order positions [grp_start[g], grp_start[g] +
- * grp_rows[g]), at most group_rows <= 32 rows that may depend on each other) and the STEPS:
- * kind 0 = one level of more than wide_min rows, order positions [step_lo, step_hi), rows
- * independent; kind 1 = groups [step_lo, step_hi), independent of each other (a band of
- * consecutive levels split into its connected components), multi-row groups first and single-row
- * groups from step_mid on, at most max_multi multi-row groups per step.  split_out[i] = first
- * entry of row i that refers to a row of its own group; for those entries col2 holds the slot
- * inside the group.  All output arrays hold n entries (rowptr2 n + 1, col2 / val2 nnz).
+ * order_out[p], which rla_sptrsv_transpose_in/out produce with perm = pos[perm_r] etc.).
+ * GROUPS (multi-row only): group g = order positions [grp_start[g], grp_start[g] + grp_rows[g]),
+ * a chain of at most group_rows <= 128 rows that depend on each other; every dependency of a
+ * group outside itself lies in an earlier level of the GROUP dependency graph.  STEPS, up to three
+ * per group level: kind 0 / kind 1 = order positions [step_lo, step_hi): each row subtracts its
+ * external entries (one warp per row / one CTA of 8 or 16 warps per row for rows of more than 64
+ * entries) and a single row divides by its diagonal; kind 2 = groups [step_lo, step_hi) are
+ * resolved.  split_out[i] = end of the external entries of row i; behind it the entries that
+ * refer to the row's own group, col2 = slot inside the group.  wide_min: levels with more rows
+ * stay single rows; max_multi is ignored (kept for ABI stability).  All output arrays hold n
+ * entries (rowptr2 n + 1, col2 / val2 nnz).
+ * rla_sptrsv_group_inverses_host (HOST): dinv_out + dinv_ptr[g] <- inverse of the triangular
+ * block of group g (row-major grp_rows[g]^2 doubles; the caller sizes dinv_ptr as the running
+ * sum of grp_rows^2), diag_eff_out[p] <- 1.0 inside groups, the diagonal elsewhere.
  * rla_sptrsv_transpose_in/out: (m, n) block of the reference layout <-> X (n, ldx) with the m
  * right-hand sides contiguous (ldx even, >= m), with the row / column permutation of the
  * factorisation applied on the way (perm_dev may be NULL): X[perm[i], c] = B[c, i] and
  * out[c, i] = X[perm[i], c].
- * rla_sptrsv_solve_f64: in-place T X = X, one or two launches per step (the step arrays stay on
- * the HOST); grp_of_pos_dev[p] = group of the row at order position p (n int32, -1 for rows of
- * kind-0 steps); grp_start_host = host copy of grp_start, grp_csum_host = running sum of grp_rows (ngroups + 1 entries, host); diag_dev NULL = unit diagonal; scratch_dev: rla_sptrsv_scratch_bytes(ldx, max_multi)
- * bytes, zero-filled once by the caller. */
+ * rla_sptrsv_solve_f64: in-place T X = X, one launch per step (the step arrays stay on the
+ * HOST, everything else on the device); diag_eff_dev NULL = no division (unit diagonal). */
 int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val,
                          int lower, int wide_min, int group_rows, int max_multi,
                          int32_t *level_out, int32_t *order_out, int32_t *pos_out,
@@ -281,14 +285,16 @@ int rla_sptrsv_transpose_in_f64(const double *b_dev, int64_t m, int64_t n, int64
                                 const int32_t *perm_dev, double *x_dev, int64_t ldx, void *stream);
 int rla_sptrsv_transpose_out_f64(const double *x_dev, int64_t m, int64_t n, int64_t ldx,
                                  const int32_t *perm_dev, double *out_dev, int64_t ldo, void *stream);
-size_t rla_sptrsv_scratch_bytes(int64_t ldx, int max_multi);
+int rla_sptrsv_group_inverses_host(int64_t n, const int64_t *rowptr2, const int32_t *col2, const double *val2,
+                                   const double *diag_in, const int64_t *split, int64_t ngroups,
+                                   const int64_t *grp_start, const int32_t *grp_rows,
+                                   const int64_t *dinv_ptr, double *dinv_out, double *diag_eff_out);
 int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *col_dev, const double *val_dev,
-                         const double *diag_dev, const int64_t *split_dev, const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
-                         const int32_t *grp_of_pos_dev, const int64_t *grp_start_host, const int64_t *grp_csum_host,
-                         const int64_t *step_lo_host, const int64_t *step_mid_host, const int64_t *step_hi_host,
-                         const int32_t *step_kind_host, int64_t nsteps, int max_multi,
-                         double *x_dev, int64_t m, int64_t ldx,
-                         void *scratch_dev, size_t scratch_bytes, void *stream);
+                         const double *diag_eff_dev, const int64_t *split_dev,
+                         const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
+                         const int64_t *dinv_ptr_dev, const double *dinv_dev,
+                         const int64_t *step_lo_host, const int64_t *step_hi_host, const int32_t *step_kind_host,
+                         int64_t nsteps, double *x_dev, int64_t m, int64_t ldx, void *stream);
 /* out[p, :] = in[map[p], :] on (n, ldx) blocks: re-ordering between the schedules of L and U */
 int rla_sptrsv_permute_rows_f64(const double *in_dev, const int32_t *map_dev, double *out_dev,
                                 int64_t n, int64_t ldx, void *stream);

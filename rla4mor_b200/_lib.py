@@ -66,10 +66,10 @@ _SIGS = {
                                      POINTER(ctypes.c_int32)]),
     "rla_sptrsv_transpose_in_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, c_int64, _vp]),
     "rla_sptrsv_transpose_out_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, c_int64, _vp]),
-    "rla_sptrsv_scratch_bytes": (c_size_t, [c_int64, c_int]),
+    "rla_sptrsv_group_inverses_host": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, c_int64, _vp, _vp, _vp, _vp, _vp]),
     "rla_sptrsv_permute_rows_f64": (c_int, [_vp, _vp, _vp, c_int64, c_int64, _vp]),
-    "rla_sptrsv_solve_f64": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int64, c_int,
-                                     _vp, c_int64, c_int64, _vp, c_size_t, _vp]),
+    "rla_sptrsv_solve_f64": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int64, _vp, c_int64,
+                                     c_int64, _vp]),
     "rla_peer_buffer_create": (c_int, [c_size_t, POINTER(c_void_p), _vp]),
     "rla_peer_buffer_open": (c_int, [_vp, POINTER(c_void_p)]),
     "rla_peer_buffer_close": (c_int, [_vp]),

@@ -10,15 +10,17 @@
 // permutation.  A row of a factor then reads, for every off-diagonal entry (i, j), the 8*m
 // contiguous bytes X[j, :] (one 512-byte request per warp at m = 64): HBM/L2-bound.
 //
-// Scheduling is by LEVEL SETS computed on the host (rla_sptrsv_plan_host): rows of one level only
-// depend on earlier levels.
-//   * wide levels: one launch per level, one warp per row and per chunk of 64 right-hand sides;
-//   * runs of narrow levels (<= 32 rows each -- the tail of the elimination tree: at n = 1e6 for a
-//     2-D FEM factor, 4800 of 5161 levels, 16e3 rows holding HALF of the entries) are cut into
-//     GROUPS of 32 consecutive rows.  One launch per group: CTA r sums the entries of row r whose
-//     columns were solved by earlier launches (8 warps, 4 loads in flight each); the last CTA to
-//     arrive (ticket counter, no spin-wait) resolves the dependencies INSIDE the group
-//     sequentially out of shared memory.  500 launches instead of 4800 sequential levels.
+// Scheduling (host, rla_sptrsv_plan_host): rows are collected into GROUPS -- chains of up to 128
+// rows that depend on each other (the supernodes of the factor) -- and the groups, together with
+// the remaining single rows, are sorted into the levels of the GROUP dependency graph (a 2-D FEM
+// factor with 5161 row levels has ~50-70 group levels).  One group level = up to three launches:
+//   * kind 1 / kind 0: every row of the level subtracts its EXTERNAL entries (columns solved in
+//     earlier levels) from its right-hand sides: one CTA of 16 warps per long row, one warp per
+//     short row; a single row also divides by its diagonal and is finished;
+//   * kind 2: one CTA per group multiplies the group's rows by the INVERSE of the group's dense
+//     triangular block (computed once on the host, rla_sptrsv_group_inverses_host): the chain of
+//     up to 128 dependent rows is resolved by one small dense product instead of 128 sequential
+//     steps -- no tickets, no fences, no partial sums through global memory.
 // Deterministic: every sum has a fixed order.
 #include "common.cuh"
 #include <algorithm>
@@ -81,15 +83,13 @@ struct TrsvArgs {
     const int64_t *rowptr;      // CSR of the strictly triangular part, rows and columns renumbered by
     const int32_t *col;         //   schedule position, entries of a row sorted by column
     const double *val;
-    const double *diag;         // diagonal by position, or null for a unit diagonal
-    const int64_t *split;       // per row: first entry whose column lies in the row's own group
+    const double *diag;         // divisor by position (1.0 for the rows of a group), or null: no division
+    const int64_t *split;       // per row: end of its external entries (the rest refers to its own group)
     double *X;
-    double *E;                  // scratch: external sums of the multi-row groups of a launch
-    unsigned int *counter;      // scratch: arrival counters (zero between launches)
     int64_t ldx, m;
 };
 
-constexpr int TRSV_GROUP = 32;                        // rows per group of the narrow tail
+constexpr int TRSV_GROUP = 128;                       // rows per group (chain of dependent rows resolved by one CTA)
 
 constexpr int TRSV_WARPS = 16;                        // warps of a CTA that owns one (long) row
 constexpr int TRSV_WARPS_SMALL = 4;                   // ... in steps of many short rows
@@ -136,26 +136,28 @@ __device__ __forceinline__ double2 row_sum_warp(const TrsvArgs &a, int64_t e0, i
     return acc;
 }
 
-// one wide level: warp = one row x one chunk of 64 right-hand sides
+// kind 0: warp = one row x one chunk of 64 right-hand sides; external entries [rowptr, split)
 __global__ void __launch_bounds__(256)
-trsv_wide_kernel(const TrsvArgs a, int64_t lo, int64_t hi) {
+trsv_rows_warp_kernel(const TrsvArgs a, int64_t lo, int64_t hi) {
     const int lane = threadIdx.x & 31;
     const int64_t idx = lo + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (idx >= hi) return;                             // whole warp
     const int64_t c = (int64_t)blockIdx.y * TRSV_RHS + 2 * lane;
     const bool live = c < a.ldx;
     const int64_t i = idx;
-    double2 acc = row_sum_warp<8>(a, a.rowptr[i], a.rowptr[i + 1], c, live, 0, 1);
+    // the row's own right-hand sides and divisor do not depend on the sum: fetch them first
+    double *xi = a.X + i * a.ldx + c;
+    const double2 b = live ? ldcg2(xi) : make_double2(0.0, 0.0);
+    const double d = a.diag ? a.diag[i] : 1.0;
+    double2 acc = row_sum_warp<8>(a, a.rowptr[i], a.split[i], c, live, 0, 1);
     if (live) {
-        double *xi = a.X + i * a.ldx + c;
-        const double2 b = *reinterpret_cast<const double2 *>(xi);
         acc.x += b.x; acc.y += b.y;
-        if (a.diag) { const double d = a.diag[i]; acc.x /= d; acc.y /= d; }
+        if (a.diag) { acc.x /= d; acc.y /= d; }
         *reinterpret_cast<double2 *>(xi) = acc;
     }
 }
 
-// the same sum with the row split over the TRSV_WARPS warps of the CTA, combined in warp order;
+// the same sum with the row split over the NW warps of the CTA, combined in warp order;
 // result valid in warp 0
 template <int NW>
 __device__ __forceinline__ double2 row_sum_cta(const TrsvArgs &a, int64_t e0, int64_t e1, int64_t c, bool live,
@@ -172,107 +174,85 @@ __device__ __forceinline__ double2 row_sum_cta(const TrsvArgs &a, int64_t e0, in
     return acc;
 }
 
-// One STEP of the schedule: a set of independent GROUPS.  A group is up to 32 rows that depend on
-// each other (a chain of consecutive levels inside one supernode of the factor) and, outside the
-// group, only on rows solved by earlier launches.  blockIdx.x = row (of some group of the launch),
-// blockIdx.y = chunk of right-hand sides.  CTA (r, chunk, g) sums the EXTERNAL entries of
-// its row with all its warps; a single-row group is finished right there; otherwise the last CTA
-// of the group to arrive (ticket counter, no spin-wait) stages the group's internal entries and
-// right-hand sides in shared memory and resolves the internal dependencies sequentially (one
-// warp, lanes = right-hand sides).  One launch per ~32 levels instead of one per level.
+// kind 1: one CTA = one LONG row (more than 64 external entries, up to thousands near the root of the
+// elimination tree) x one chunk of right-hand sides.  NW = 16 warps with 16 loads in flight each
+// when the step has few rows (all the parallelism must come from inside the row), 8 warps x 8
+// loads and four CTAs per SM when it has many.
 template <int NW>
-__global__ void __launch_bounds__(32 * NW, NW >= 16 ? 1 : 8)
-trsv_groups_kernel(const TrsvArgs a, const int64_t *__restrict__ grp_start, const int32_t *__restrict__ grp_rows,
-                   const int32_t *__restrict__ grp_of_pos, int64_t g_first, int64_t p_first) {
+__global__ void __launch_bounds__(32 * NW, NW >= 16 ? 1 : 4)
+trsv_rows_cta_kernel(const TrsvArgs a, int64_t lo) {
     __shared__ double2 part[NW][32];
-    __shared__ double2 xs[2][32];                      // x of the row just resolved, double buffered
-    __shared__ double D[TRSV_GROUP][TRSV_GROUP + 1];   // dense image of the group's internal entries
-    __shared__ double s_diag[TRSV_GROUP];
-    __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // CTA <-> one row: order position p_first + blockIdx.x (the rows of the groups of a launch are
-    // contiguous in the order), no idle CTAs
-    const int64_t p = p_first + blockIdx.x;
-    const int64_t gid = grp_of_pos[p];
-    const int nrows = grp_rows[gid];
-    const int64_t g0 = grp_start[gid];
-    const int r = (int)(p - g0);
-    const int64_t eslot = gid - g_first;               // multi-row groups of a launch: scratch slot
+    const int64_t i = lo + blockIdx.x;
     const int64_t c = (int64_t)blockIdx.y * TRSV_RHS + 2 * lane;
     const bool live = c < a.ldx;
-    const int64_t i = p;
+    double *xi = a.X + i * a.ldx + c;
+    double2 b = make_double2(0.0, 0.0);
+    double d = 1.0;
+    if (warp == 0) {
+        if (live) b = ldcg2(xi);
+        if (a.diag) d = a.diag[i];
+    }
     double2 acc = row_sum_cta<NW>(a, a.rowptr[i], a.split[i], c, live, part);
-    if (nrows == 1) {                                  // nothing internal: finish the row here
-        if (warp == 0 && live) {
-            double *xi = a.X + i * a.ldx + c;
-            const double2 b = *reinterpret_cast<const double2 *>(xi);
-            acc.x += b.x; acc.y += b.y;
-            if (a.diag) { const double d = a.diag[i]; acc.x /= d; acc.y /= d; }
-            *reinterpret_cast<double2 *>(xi) = acc;
-        }
-        return;
+    if (warp == 0 && live) {
+        acc.x += b.x; acc.y += b.y;
+        if (a.diag) { acc.x /= d; acc.y /= d; }
+        *reinterpret_cast<double2 *>(xi) = acc;
     }
-    double *E = a.E + eslot * TRSV_GROUP * a.ldx;
-    unsigned int *counter = a.counter + eslot * gridDim.y + blockIdx.y;
-    if (warp == 0) {                                   // the writers fence, then one thread takes the ticket
-        if (live) *reinterpret_cast<double2 *>(E + (int64_t)r * a.ldx + c) = acc;
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-            const unsigned int ticket = atomicAdd(counter, 1u);
-            s_last = ticket == (unsigned int)nrows - 1;
-            if (s_last) {
-                *counter = 0;                          // ready for the next launch
-                __threadfence();
+}
+
+// kind 2: one CTA per group and chunk of right-hand sides.  The rows of the group hold
+// y = b - (external sums); x = Dinv y with the inverse of the group's triangular block (row-major
+// nrows x nrows at dinv + dinv_ptr[g], lower triangle).  y is staged in shared memory (lanes =
+// pairs of right-hand sides); warp w owns rows w, w + 16, ...: the entries of a row of Dinv come in
+// with one coalesced load per 32 and are broadcast by shuffles.
+__global__ void __launch_bounds__(32 * TRSV_WARPS, 2)
+trsv_resolve_kernel(double *__restrict__ X, int64_t ldx, const int64_t *__restrict__ grp_start,
+                    const int32_t *__restrict__ grp_rows, const int64_t *__restrict__ dinv_ptr,
+                    const double *__restrict__ dinv, int64_t g_first) {
+    extern __shared__ __align__(16) double2 ys[];      // [nrows][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gid = g_first + blockIdx.x;
+    const int nrows = grp_rows[gid];
+    const int64_t g0 = grp_start[gid];
+    const double *Dg = dinv + dinv_ptr[gid];
+    const int64_t c = (int64_t)blockIdx.y * TRSV_RHS + 2 * lane;
+    const bool live = c < ldx;
+    for (int q = warp; q < nrows; q += TRSV_WARPS)
+        ys[q * 32 + lane] = live ? ldcg2(X + (g0 + q) * ldx + c) : make_double2(0.0, 0.0);
+    __syncthreads();
+    // Warp w owns rows w, w + 16, ..., longest first.  The (up to four) 32-entry pieces of a row of Dinv
+    // are fetched in one go, and the next row's pieces while this row is multiplied: the loads are
+    // never on the critical path.
+    constexpr int NP = TRSV_GROUP / 32;
+    auto fetch = [&](int r, double (&dv)[NP]) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const int q = 32 * k + lane;
+            dv[k] = (r >= 0 && q <= r) ? __ldg(Dg + (int64_t)r * nrows + q) : 0.0;
+        }
+    };
+    int r = nrows - 1 >= warp ? warp + ((nrows - 1 - warp) / TRSV_WARPS) * TRSV_WARPS : -1;
+    double dv[NP], dn[NP];
+    fetch(r, dv);
+    for (; r >= 0; r -= TRSV_WARPS) {
+        fetch(r - TRSV_WARPS, dn);
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const int q0 = 32 * k;
+            if (q0 <= r) {
+                const int cnt = min(32, r + 1 - q0);
+                for (int u = 0; u < cnt; ++u) {
+                    const double v = __shfl_sync(0xffffffffu, dv[k], u);
+                    const double2 y = ys[(q0 + u) * 32 + lane];
+                    acc.x = fma(v, y.x, acc.x); acc.y = fma(v, y.y, acc.y);
+                }
             }
         }
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // Stage the group: its internal entries as a dense 32 x 32 lower-triangular image D, and
-    // b + external sum of the two rows (warp, warp + 16) this warp owns, in registers.
-    constexpr int RPW = TRSV_GROUP / NW;               // rows of the group per warp: q = warp + h * NW
-    for (int t = threadIdx.x; t < TRSV_GROUP * (TRSV_GROUP + 1); t += blockDim.x) (&D[0][0])[t] = 0.0;
-    if (threadIdx.x < nrows) s_diag[threadIdx.x] = a.diag ? a.diag[g0 + threadIdx.x] : 1.0;
-    __syncthreads();
-    double2 acc2[RPW];
+        if (live) *reinterpret_cast<double2 *>(X + (g0 + r) * ldx + c) = acc;
 #pragma unroll
-    for (int h = 0; h < RPW; ++h) {
-        const int q = warp + h * NW;
-        acc2[h] = make_double2(0.0, 0.0);
-        if (q < nrows) {
-            const int64_t iq = g0 + q;
-            const int64_t e0 = a.split[iq];
-            const int cnt = (int)(a.rowptr[iq + 1] - e0);
-            for (int t = lane; t < cnt; t += 32) D[q][a.col[e0 + t]] = a.val[e0 + t];
-            if (live) {
-                const double2 b = ldcg2(a.X + iq * a.ldx + c), ext = ldcg2(E + (int64_t)q * a.ldx + c);
-                acc2[h] = make_double2(b.x + ext.x, b.y + ext.y);
-            }
-        }
-    }
-    __syncthreads();
-    // Right-looking resolve: row q becomes final, every later row subtracts its entry (r, q) times
-    // x_q.  One CTA barrier per row, rows spread over the warps, lanes = right-hand sides.
-    for (int q = 0; q < nrows; ++q) {
-        if ((q % NW) == warp) {
-            double2 x = acc2[0];                       // acc2[q / NW] with static register indices
-#pragma unroll
-            for (int h = 1; h < RPW; ++h) if (q >= h * NW) x = acc2[h];
-            if (a.diag) { const double d = s_diag[q]; x.x /= d; x.y /= d; }
-            xs[q & 1][lane] = x;
-            if (live) *reinterpret_cast<double2 *>(a.X + (g0 + q) * a.ldx + c) = x;
-        }
-        __syncthreads();
-        const double2 x = xs[q & 1][lane];
-#pragma unroll
-        for (int h = 0; h < RPW; ++h) {
-            const int r2 = warp + h * NW;
-            if (r2 > q && r2 < nrows) {
-                const double v = D[r2][q];
-                acc2[h].x = fma(-v, x.x, acc2[h].x); acc2[h].y = fma(-v, x.y, acc2[h].y);
-            }
-        }
+        for (int k = 0; k < NP; ++k) dv[k] = dn[k];
     }
 }
 
@@ -286,14 +266,14 @@ using namespace rla;
 //   rowptr2/col2/val2  the strictly triangular part, entries of each row sorted by pos[col]
 //   diag_out       the diagonal (1.0 where absent)
 //   groups         group g = order positions [grp_start[g], grp_start[g] + grp_rows[g]), <= group_rows rows
-//   steps          kind 0: ONE level of more than `wide_min` rows, order positions [step_lo, step_hi),
-//                  rows independent; kind 1: groups [step_lo, step_hi), independent of each other, the
-//                  multi-row groups first, then (from step_mid on) the single-row groups.
+//   groups         MULTI-ROW groups only: group g = order positions [grp_start[g], + grp_rows[g])
+//   steps          kind 0 / kind 1: order positions [step_lo, step_hi): every row subtracts its external
+//                  entries (one warp / one CTA of 16 warps per row) and, if it is a single row, divides
+//                  by its diagonal; kind 2: groups [step_lo, step_hi) are resolved (x = Dinv y).
+//                  Up to three steps per level of the GROUP dependency graph; step_mid = step_hi.
 //   split_out[i]   first entry of row i that refers to a row of its own group (row end when there is
 //                  none); for those entries col2 holds the slot of the column inside the group.
-// A kind-1 step is a BAND of up to `group_rows` consecutive levels whose connected components
-// (dependencies inside the band) all have at most `group_rows` rows: each component is a group.  The
-// band is shortened until that holds (a single level always qualifies: singleton groups).  At most
+// Groups are CHAINS of up to `group_rows` dependent rows (see the grouping loop below); at most
 // max_multi multi-row groups per step (they need scratch).  Arrays of n entries each.
 extern "C" int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val,
                                     int lower, int wide_min, int group_rows, int max_multi,
@@ -333,107 +313,127 @@ extern "C" int rla_sptrsv_plan_host(int64_t n, const int64_t *rowptr, const int3
             pos_out[i] = (int32_t)p;
         }
     }
+    // ---- groups: CHAINS instead of global bands of levels.
+    // Rows are visited in level order.  Row i joins the group G of its deepest dependency when G has
+    // room and every other dependency outside G lies strictly below G's first level; else it opens a
+    // group of its own.  All external dependencies of a group then have a level below the group's
+    // first level, so (a) groups sorted by first level are in topological order and (b) the group
+    // DAG has its own levels `glevel`: one STEP per group level instead of one per band of row
+    // levels.  A chain of 32 dependent rows (a supernode of the factor) is ONE group whatever the
+    // rest of the matrix looks like at those levels: the critical path of a 2-D FEM factor drops
+    // from ~800 steps (bands cut short by unrelated components) to levels / 32.
+    // Rows of wide levels (> wide_min rows: the leaves of the elimination tree) stay single and closed.
     std::vector<int64_t> gstart_of_pos((size_t)n, -1);  // start position of the group of the row at a position
-    std::vector<int32_t> parent, csize, band_rows, comp_first;
-    int64_t ns = 0, ng = 0;
-    int32_t l = 0;
-    while (l < nl) {
-        const int64_t rows = lvlptr[(size_t)l + 1] - lvlptr[l];
-        if (rows > wide_min) {
-            step_lo[ns] = lvlptr[l]; step_mid[ns] = lvlptr[(size_t)l + 1]; step_hi[ns] = lvlptr[(size_t)l + 1];
-            step_kind[ns] = 0; ++ns;
-            ++l;
-            continue;
+    std::vector<int32_t> gid((size_t)n, -1), gsize, gminlevel;
+    std::vector<char> gclosed;
+    std::vector<int32_t> ord0(order_out, order_out + n);               // level order
+    auto new_group = [&](int64_t i, bool closed) {
+        gid[i] = (int32_t)gsize.size();
+        gsize.push_back(1); gminlevel.push_back(level_out[i]); gclosed.push_back(closed ? 1 : 0);
+    };
+    for (int64_t q = 0; q < n; ++q) {
+        const int64_t i = ord0[q];
+        const int32_t li = level_out[i];
+        if (lvlptr[(size_t)li + 1] - lvlptr[li] > wide_min) { new_group(i, true); continue; }
+        int64_t best = -1;
+        for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+            const int32_t j = col[e];
+            if (j != i && (best < 0 || level_out[j] > level_out[best])) best = j;
         }
-        // longest band [l, l + W) of non-wide levels whose components have at most group_rows rows
-        int32_t W = 1;
-        while (W < group_rows && l + W < nl && lvlptr[(size_t)l + W + 1] - lvlptr[(size_t)l + W] <= wide_min) ++W;
-        const int64_t p0 = lvlptr[l];
-        for (;; W = std::max(1, W / 2)) {
-            const int64_t p1 = lvlptr[(size_t)l + W];
-            const int64_t nb = p1 - p0;
-            parent.resize((size_t)nb); csize.assign((size_t)nb, 1);
-            for (int64_t t = 0; t < nb; ++t) parent[t] = (int32_t)t;
-            bool ok = true;
-            if (W > 1) {
-                auto find = [&](int32_t x) {
-                    while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
-                    return x;
-                };
-                for (int64_t p = p0; p < p1 && ok; ++p) {
-                    const int64_t i = order_out[p];
-                    for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
-                        const int32_t j = col[e];
-                        if (j == i || pos_out[j] < p0) continue;      // outside the band (earlier levels)
-                        int32_t ra = find((int32_t)(p - p0)), rb = find((int32_t)(pos_out[j] - p0));
-                        if (ra == rb) continue;
-                        if (csize[ra] < csize[rb]) std::swap(ra, rb);
-                        parent[rb] = ra;
-                        csize[ra] += csize[rb];
-                        if (csize[ra] > group_rows) { ok = false; break; }
-                    }
-                }
-                if (ok) for (int64_t t = 0; t < nb; ++t) parent[t] = find((int32_t)t);
+        if (best < 0) { new_group(i, false); continue; }
+        const int32_t g = gid[best];
+        bool ok = !gclosed[g] && gsize[g] < group_rows;
+        for (int64_t e = rowptr[i]; ok && e < rowptr[i + 1]; ++e) {
+            const int32_t j = col[e];
+            if (j != i && gid[j] != g && level_out[j] >= gminlevel[g]) ok = false;
+        }
+        if (ok) { gid[i] = g; ++gsize[g]; } else new_group(i, false);
+    }
+    const int64_t ngr = (int64_t)gsize.size();
+    // rows of every group, in level order (= a topological order of the group's internal dependencies)
+    std::vector<int64_t> gptr((size_t)ngr + 1, 0);
+    for (int64_t g = 0; g < ngr; ++g) gptr[(size_t)g + 1] = gptr[g] + gsize[g];
+    std::vector<int32_t> grow((size_t)n);
+    {
+        std::vector<int64_t> fill(gptr.begin(), gptr.end() - 1);
+        for (int64_t q = 0; q < n; ++q) { const int64_t i = ord0[q]; grow[fill[gid[i]]++] = (int32_t)i; }
+    }
+    // group levels: groups were created in level order of their first row = topological order
+    std::vector<int32_t> glevel((size_t)ngr, 0);
+    std::vector<int64_t> gmaxlen((size_t)ngr, 0), gext((size_t)ngr, 0);
+    int32_t ngl = 0;
+    for (int64_t g = 0; g < ngr; ++g) {
+        int32_t gl = 0;
+        for (int64_t t = gptr[g]; t < gptr[(size_t)g + 1]; ++t) {
+            const int64_t i = grow[t];
+            gmaxlen[g] = std::max<int64_t>(gmaxlen[g], rowptr[i + 1] - rowptr[i]);
+            for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+                const int32_t j = col[e];
+                if (j != i && gid[j] != g) { gl = std::max(gl, glevel[gid[j]] + 1); ++gext[g]; }
             }
-            if (!ok) continue;                                         // shorten the band
-            // accepted: components -> groups; rows of a component stay in level order (stable)
-            band_rows.resize((size_t)nb);
-            for (int64_t t = 0; t < nb; ++t) band_rows[t] = order_out[p0 + t];
-            // multi-row components first (in order of first appearance), then singletons
-            comp_first.assign((size_t)nb, -1);
-            std::vector<std::vector<int32_t>> multi;
-            std::vector<int32_t> single;
-            for (int64_t t = 0; t < nb; ++t) {
-                const int32_t root = parent[t];
-                if (csize[root] == 1) { single.push_back((int32_t)t); continue; }
-                if (comp_first[root] < 0) { comp_first[root] = (int32_t)multi.size(); multi.emplace_back(); }
-                multi[comp_first[root]].push_back((int32_t)t);
-            }
-            // longest rows first: a step ends with its slowest CTA, so the long rows (ancestor
-            // separators) must start at once instead of queueing behind thousands of short ones
-            auto rowlen = [&](int32_t t) { const int64_t i = band_rows[t]; return rowptr[i + 1] - rowptr[i]; };
-            std::vector<int64_t> mlen(multi.size(), 0);
-            for (size_t g = 0; g < multi.size(); ++g)
-                for (int32_t t : multi[g]) mlen[g] = std::max(mlen[g], rowlen(t));
-            std::vector<size_t> mord(multi.size());
-            for (size_t g = 0; g < multi.size(); ++g) mord[g] = g;
-            std::stable_sort(mord.begin(), mord.end(), [&](size_t x, size_t y) { return mlen[x] > mlen[y]; });
-            {
-                std::vector<std::vector<int32_t>> sorted;
-                sorted.reserve(multi.size());
-                for (size_t g : mord) sorted.push_back(std::move(multi[g]));
-                multi.swap(sorted);
-            }
-            std::stable_sort(single.begin(), single.end(), [&](int32_t x, int32_t y) { return rowlen(x) > rowlen(y); });
-            int64_t p = p0;
-            size_t mi = 0, si = 0;
-            // emit steps: at most max_multi multi-row groups (and at most 65535 groups) per step
-            while (mi < multi.size() || si < single.size()) {
-                step_kind[ns] = 1;
-                step_lo[ns] = ng;
-                size_t took = 0;
-                for (; mi < multi.size() && took < (size_t)max_multi; ++mi, ++took) {
-                    grp_start[ng] = p; grp_rows[ng] = (int32_t)multi[mi].size();
-                    for (int32_t t : multi[mi]) {
-                        order_out[p] = band_rows[t]; pos_out[band_rows[t]] = (int32_t)p; gstart_of_pos[p] = grp_start[ng];
-                        ++p;
-                    }
-                    ++ng;
-                }
-                step_mid[ns] = ng;
-                if (mi == multi.size()) {
-                    for (took = 0; si < single.size() && took < 65535; ++si, ++took) {
-                        const int32_t t = single[si];
-                        grp_start[ng] = p; grp_rows[ng] = 1;
-                        order_out[p] = band_rows[t]; pos_out[band_rows[t]] = (int32_t)p; gstart_of_pos[p] = p;
-                        ++p; ++ng;
-                    }
-                }
-                step_hi[ns] = ng;
-                ++ns;
-            }
-            l += W;
-            break;
+        }
+        glevel[g] = gl;
+        ngl = std::max(ngl, gl + 1);
+    }
+    // bucket the groups by group level
+    std::vector<int64_t> glptr((size_t)ngl + 1, 0);
+    for (int64_t g = 0; g < ngr; ++g) ++glptr[(size_t)glevel[g] + 1];
+    for (int32_t l = 0; l < ngl; ++l) glptr[(size_t)l + 1] += glptr[l];
+    std::vector<int32_t> gsorted((size_t)ngr);
+    {
+        std::vector<int64_t> fill(glptr.begin(), glptr.end() - 1);
+        for (int64_t g = 0; g < ngr; ++g) gsorted[fill[glevel[g]]++] = (int32_t)g;
+    }
+    int64_t ns = 0, ng = 0, p = 0;
+    std::vector<int32_t> multi, single;
+    auto place_group = [&](int32_t g) {                 // rows of group g take the next positions of the order
+        grp_start[ng] = p; grp_rows[ng] = gsize[g];
+        for (int64_t t = gptr[g]; t < gptr[(size_t)g + 1]; ++t) {
+            const int32_t i = grow[t];
+            order_out[p] = i; pos_out[i] = (int32_t)p; gstart_of_pos[p] = grp_start[ng];
+            ++p;
+        }
+        ++ng;
+    };
+    // One group level = up to three steps: kind 1 (CTA of 16 warps per row) over the rows of the groups /
+    // single rows whose longest row exceeds LONG_ROW entries, kind 0 (warp per row) over the others, then
+    // kind 2 (one CTA per group) over the level's multi-row groups.  A 1500-entry row summed by ONE warp
+    // would cost ~190 us of dependent 512-byte loads and hold up its whole level (a warp keeps 8 loads in flight).
+    constexpr int64_t LONG_ROW = 64;
+    std::vector<int32_t> multi_s, single_s;
+    (void)max_multi;
+    for (int32_t gl = 0; gl < ngl; ++gl) {
+        multi.clear(); single.clear(); multi_s.clear(); single_s.clear();
+        for (int64_t t = glptr[gl]; t < glptr[(size_t)gl + 1]; ++t) {
+            const int32_t g = gsorted[t];
+            const bool lng = gmaxlen[g] > LONG_ROW;
+            (gsize[g] > 1 ? (lng ? multi : multi_s) : (lng ? single : single_s)).push_back(g);
+        }
+        // longest rows first: a step ends with its slowest CTA
+        auto by_len = [&](int32_t x, int32_t y) { return gmaxlen[x] > gmaxlen[y]; };
+        std::stable_sort(multi.begin(), multi.end(), by_len);
+        std::stable_sort(single.begin(), single.end(), by_len);
+        const int64_t g_lo = ng;
+        auto place_single = [&](int32_t g) {
+            const int32_t i = grow[gptr[g]];
+            order_out[p] = i; pos_out[i] = (int32_t)p; gstart_of_pos[p] = -1;
+            ++p;
+        };
+        auto emit_rows = [&](int kind, const std::vector<int32_t> &mg, const std::vector<int32_t> &sg) {
+            if (mg.empty() && sg.empty()) return;
+            step_kind[ns] = kind;
+            step_lo[ns] = p;
+            for (int32_t g : mg) place_group(g);
+            for (int32_t g : sg) place_single(g);
+            step_mid[ns] = p; step_hi[ns] = p;
+            ++ns;
+        };
+        emit_rows(1, multi, single);
+        emit_rows(0, multi_s, single_s);
+        if (ng > g_lo) {
+            step_kind[ns] = 2;
+            step_lo[ns] = g_lo; step_mid[ns] = ng; step_hi[ns] = ng;
+            ++ns;
         }
     }
     *nsteps_out = ns;
@@ -491,64 +491,94 @@ extern "C" int rla_sptrsv_transpose_out_f64(const double *x_dev, int64_t m, int6
     return RLA_OK;
 }
 
-// In-place triangular solve T X = X on the (n, ldx) block (right-hand sides contiguous), driven by
-// the step list of rla_sptrsv_plan_host (HOST arrays step_*); all other arrays on the device.
-// scratch_dev: rla_sptrsv_scratch_bytes(ldx, max_multi) bytes, zero-filled once by the caller.
-extern "C" size_t rla_sptrsv_scratch_bytes(int64_t ldx, int max_multi) {
-    const size_t chunks = (size_t)((ldx + TRSV_RHS - 1) / TRSV_RHS);
-    return (size_t)max_multi * ((size_t)TRSV_GROUP * (size_t)ldx * sizeof(double) + chunks * sizeof(unsigned int)) + 64;
+// Inverses of the groups' triangular blocks (HOST, once per factor).  Group g holds the rows at
+// positions [grp_start[g], + grp_rows[g]); its block D has diag_in[p] on the diagonal and the row's
+// internal entries (col2 = slot inside the group) below it.  dinv_out + dinv_ptr[g] receives
+// D^-1 row-major (nrows x nrows, upper triangle zero) by forward substitution, column by column;
+// diag_eff_out[p] = 1.0 for the rows of a group (their division is inside D^-1), diag_in[p] else.
+extern "C" int rla_sptrsv_group_inverses_host(int64_t n, const int64_t *rowptr2, const int32_t *col2, const double *val2,
+                                              const double *diag_in, const int64_t *split, int64_t ngroups,
+                                              const int64_t *grp_start, const int32_t *grp_rows,
+                                              const int64_t *dinv_ptr, double *dinv_out, double *diag_eff_out) {
+    RLA_REQUIRE(n >= 0 && ngroups >= 0 && rowptr2 && diag_in && split && diag_eff_out &&
+                (ngroups == 0 || (grp_start && grp_rows && dinv_ptr && dinv_out)), "rla_sptrsv_group_inverses_host: null pointer");
+    for (int64_t q = 0; q < n; ++q) diag_eff_out[q] = diag_in[q];
+    std::vector<double> D;
+    for (int64_t g = 0; g < ngroups; ++g) {
+        const int64_t g0 = grp_start[g];
+        const int nr = grp_rows[g];
+        RLA_REQUIRE(nr >= 1 && nr <= TRSV_GROUP && g0 >= 0 && g0 + nr <= n, "rla_sptrsv_group_inverses_host: bad group %lld", (long long)g);
+        D.assign((size_t)nr * nr, 0.0);
+        for (int r = 0; r < nr; ++r) {
+            const int64_t q = g0 + r;
+            D[(size_t)r * nr + r] = diag_in[q];
+            RLA_REQUIRE(diag_in[q] != 0.0, "rla_sptrsv_group_inverses_host: zero diagonal at position %lld", (long long)q);
+            for (int64_t e = split[q]; e < rowptr2[q + 1]; ++e) {
+                RLA_REQUIRE(col2[e] >= 0 && col2[e] < r, "rla_sptrsv_group_inverses_host: internal entry outside the group");
+                D[(size_t)r * nr + col2[e]] = val2[e];
+            }
+            diag_eff_out[q] = 1.0;
+        }
+        double *W = dinv_out + dinv_ptr[g];
+        for (int c = 0; c < nr; ++c) {                  // column c of the inverse: D w = e_c
+            for (int r = 0; r < c; ++r) W[(size_t)r * nr + c] = 0.0;
+            for (int r = c; r < nr; ++r) {
+                double acc = r == c ? 1.0 : 0.0;
+                const double *Dr = D.data() + (size_t)r * nr;
+                for (int k = c; k < r; ++k) acc -= Dr[k] * W[(size_t)k * nr + c];
+                W[(size_t)r * nr + c] = acc / Dr[r];
+            }
+        }
+    }
+    return RLA_OK;
 }
 
+// In-place triangular solve T X = X on the (n, ldx) block (right-hand sides contiguous, rows in
+// schedule order), driven by the step list of rla_sptrsv_plan_host (HOST arrays step_*); all other
+// arrays on the device.  diag_eff_dev: divisor per position (rla_sptrsv_group_inverses_host), or NULL
+// when every divisor is 1 (unit-diagonal factor).
 extern "C" int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *col_dev, const double *val_dev,
-                                    const double *diag_dev, const int64_t *split_dev, const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
-                                    const int32_t *grp_of_pos_dev, const int64_t *grp_start_host, const int64_t *grp_csum_host,
-                                    const int64_t *step_lo, const int64_t *step_mid, const int64_t *step_hi,
-                                    const int32_t *step_kind, int64_t nsteps, int max_multi,
-                                    double *x_dev, int64_t m, int64_t ldx,
-                                    void *scratch_dev, size_t scratch_bytes, void *stream) {
-    RLA_REQUIRE(nsteps >= 0 && m >= 0 && ldx >= m && (ldx & 1) == 0 && max_multi >= 1, "rla_sptrsv_solve_f64: bad sizes");
+                                    const double *diag_eff_dev, const int64_t *split_dev,
+                                    const int64_t *grp_start_dev, const int32_t *grp_rows_dev,
+                                    const int64_t *dinv_ptr_dev, const double *dinv_dev,
+                                    const int64_t *step_lo, const int64_t *step_hi, const int32_t *step_kind,
+                                    int64_t nsteps, double *x_dev, int64_t m, int64_t ldx, void *stream) {
+    RLA_REQUIRE(nsteps >= 0 && m >= 0 && ldx >= m && (ldx & 1) == 0, "rla_sptrsv_solve_f64: bad sizes");
     if (nsteps == 0 || m == 0) return RLA_OK;
-    RLA_REQUIRE(rowptr_dev && col_dev && val_dev && split_dev && grp_start_dev && grp_rows_dev &&
-                grp_of_pos_dev && grp_start_host && grp_csum_host && step_lo && step_mid && step_hi && step_kind && x_dev && scratch_dev, "rla_sptrsv_solve_f64: null pointer");
-    RLA_REQUIRE(((uintptr_t)x_dev & 15) == 0 && ((uintptr_t)scratch_dev & 15) == 0,
-                "rla_sptrsv_solve_f64: X and scratch must be 16-byte aligned");
-    if (scratch_bytes < rla_sptrsv_scratch_bytes(ldx, max_multi))
-        return fail(RLA_ERR_WORKSPACE, "rla_sptrsv_solve_f64: scratch too small");
+    RLA_REQUIRE(rowptr_dev && col_dev && val_dev && split_dev && step_lo && step_hi && step_kind && x_dev,
+                "rla_sptrsv_solve_f64: null pointer");
+    RLA_REQUIRE(((uintptr_t)x_dev & 15) == 0, "rla_sptrsv_solve_f64: X must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    double *E = static_cast<double *>(scratch_dev);
-    unsigned int *counter = reinterpret_cast<unsigned int *>(E + (size_t)max_multi * TRSV_GROUP * ldx);
-    TrsvArgs a = {rowptr_dev, col_dev, val_dev, diag_dev, split_dev, x_dev, E, counter, ldx, m};
+    TrsvArgs a = {rowptr_dev, col_dev, val_dev, diag_eff_dev, split_dev, x_dev, ldx, m};
     const unsigned chunks = (unsigned)((ldx + TRSV_RHS - 1) / TRSV_RHS);
     RLA_REQUIRE(chunks <= 65535, "rla_sptrsv_solve_f64: too many right-hand sides");
+    static bool attr_set = false;
+    const int resolve_smem = TRSV_GROUP * 32 * (int)sizeof(double2);
+    if (!attr_set) {
+        RLA_CUDA_CHECK(cudaFuncSetAttribute(trsv_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, resolve_smem));
+        attr_set = true;
+    }
     for (int64_t s = 0; s < nsteps; ++s) {
+        const int64_t cnt = step_hi[s] - step_lo[s];
+        RLA_REQUIRE(cnt >= 1, "rla_sptrsv_solve_f64: empty step %lld", (long long)s);
         if (step_kind[s] == 0) {
-            const int64_t rows = step_hi[s] - step_lo[s];
-            RLA_REQUIRE(rows >= 1, "rla_sptrsv_solve_f64: empty step %lld", (long long)s);
-            dim3 grid((unsigned)((rows + 7) / 8), chunks);
-            trsv_wide_kernel<<<grid, 256, 0, st>>>(a, step_lo[s], step_hi[s]);
-            count_launch();
-            continue;
+            dim3 grid((unsigned)((cnt + 7) / 8), chunks);
+            trsv_rows_warp_kernel<<<grid, 256, 0, st>>>(a, step_lo[s], step_hi[s]);
+        } else if (step_kind[s] == 1) {
+            RLA_REQUIRE(cnt < (int64_t(1) << 31), "rla_sptrsv_solve_f64: step too large");
+            dim3 grid((unsigned)cnt, chunks);
+            if (cnt * chunks <= 2 * (int64_t)sm_count()) trsv_rows_cta_kernel<16><<<grid, 32 * 16, 0, st>>>(a, step_lo[s]);
+            else trsv_rows_cta_kernel<8><<<grid, 32 * 8, 0, st>>>(a, step_lo[s]);
+        } else if (step_kind[s] == 2) {
+            RLA_REQUIRE(grp_start_dev && grp_rows_dev && dinv_ptr_dev && dinv_dev && cnt < (int64_t(1) << 31),
+                        "rla_sptrsv_solve_f64: group arrays missing");
+            dim3 grid((unsigned)cnt, chunks);
+            trsv_resolve_kernel<<<grid, 32 * TRSV_WARPS, resolve_smem, st>>>(x_dev, ldx, grp_start_dev, grp_rows_dev,
+                                                                            dinv_ptr_dev, dinv_dev, step_lo[s]);
+        } else {
+            return fail(RLA_ERR_INVALID, "rla_sptrsv_solve_f64: unknown step kind %d", step_kind[s]);
         }
-        const int64_t nmulti = step_mid[s] - step_lo[s], nsingle = step_hi[s] - step_mid[s];
-        RLA_REQUIRE(nmulti >= 0 && nsingle >= 0 && nmulti <= max_multi && nsingle <= 65535 && nmulti + nsingle >= 1,
-                    "rla_sptrsv_solve_f64: bad step %lld", (long long)s);
-        // the rows of the groups of a step are contiguous in the order: multi-row groups first
-        // (grp_csum_host = running sum of grp_rows, ngroups + 1 entries), then the single rows
-        const int64_t p0 = grp_start_host[step_lo[s]];
-        const int64_t rows_multi = grp_csum_host[step_mid[s]] - grp_csum_host[step_lo[s]];
-        {
-            const int64_t rows = rows_multi + nsingle;
-            dim3 grid((unsigned)rows, chunks);                        // one launch: multi-row groups, then single rows
-            // few rows (near the root of the elimination tree, long rows): 16 warps share a row;
-            // many rows (short): 4 warps per row so that every CTA of the step is resident at once
-            if (rows < 1024)
-                trsv_groups_kernel<TRSV_WARPS><<<grid, 32 * TRSV_WARPS, 0, st>>>(a, grp_start_dev, grp_rows_dev,
-                                                                                grp_of_pos_dev, step_lo[s], p0);
-            else
-                trsv_groups_kernel<TRSV_WARPS_SMALL><<<grid, 32 * TRSV_WARPS_SMALL, 0, st>>>(
-                    a, grp_start_dev, grp_rows_dev, grp_of_pos_dev, step_lo[s], p0);
-            count_launch();
-        }
+        count_launch();
     }
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;

@@ -47,7 +47,7 @@ def operator_to_cholesky(operator=None, factor=None):
     return MatrixOperator(M, source_id, range_id)
 
 
-def plan_triangular(T, lower, wide_min=4096, group=32, max_multi=256):
+def plan_triangular(T, lower, wide_min=4096, group=128, max_multi=0):
     """Host analysis of one triangular factor (C++ in librla_b200.so, no GPU involved): dict of
     NumPy arrays -- see rla_sptrsv_plan_host in include/rla_b200.h."""
     T = T.tocsr()
@@ -66,7 +66,7 @@ def plan_triangular(T, lower, wide_min=4096, group=32, max_multi=256):
     step_kind = np.empty(n1, dtype=np.int32)
     nsteps, ngroups, nlev = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
     check(lib().rla_sptrsv_plan_host(n, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, 1 if lower else 0,
-                                     int(wide_min), int(group), int(max_multi),
+                                     int(wide_min), int(group), max(1, int(max_multi)),
                                      level.ctypes.data, order.ctypes.data, pos.ctypes.data,
                                      rowptr2.ctypes.data, col2.ctypes.data, val2.ctypes.data, diag.ctypes.data,
                                      split.ctypes.data, grp_start.ctypes.data, grp_rows.ctypes.data, ctypes.byref(ngroups),
@@ -75,7 +75,17 @@ def plan_triangular(T, lower, wide_min=4096, group=32, max_multi=256):
           "rla_sptrsv_plan_host")
     ns, ng, nz = int(nsteps.value), int(ngroups.value), int(rowptr2[n])
     c = np.ascontiguousarray
+    # inverses of the groups' triangular blocks (host, once per factor) and the effective divisors
+    sizes = grp_rows[:ng].astype(np.int64)
+    dinv_ptr = np.concatenate([[0], np.cumsum(sizes * sizes)]).astype(np.int64)
+    dinv = np.empty(max(int(dinv_ptr[-1]), 1), dtype=np.float64)
+    diag_eff = np.empty(n1, dtype=np.float64)
+    check(lib().rla_sptrsv_group_inverses_host(n, rowptr2.ctypes.data, col2.ctypes.data, val2.ctypes.data,
+                                               diag.ctypes.data, split.ctypes.data, ng, grp_start.ctypes.data,
+                                               grp_rows.ctypes.data, dinv_ptr.ctypes.data, dinv.ctypes.data,
+                                               diag_eff.ctypes.data), "rla_sptrsv_group_inverses_host")
     return dict(n=n, nlevels=int(nlev.value), nsteps=ns, ngroups=ng, max_multi=int(max_multi),
+                dinv_ptr=dinv_ptr, dinv=dinv, diag_eff=diag_eff[:n],
                 level=level[:n], order=order[:n], pos=pos[:n],
                 rowptr=rowptr2, col=col2[:max(nz, 1)], val=val2[:max(nz, 1)], nnz=nz, diag=diag[:n], split=split[:n],
                 grp_start=c(grp_start[:max(ng, 1)]), grp_rows=c(grp_rows[:max(ng, 1)]),
@@ -83,54 +93,38 @@ def plan_triangular(T, lower, wide_min=4096, group=32, max_multi=256):
 
 
 class TriangularFactor:
-    """One triangular CSR matrix on the device with its schedule (levels, bands of levels split
-    into independent groups: plan_triangular)."""
+    """One triangular CSR matrix on the device with its schedule (chains of dependent rows as
+    groups, levels of the group dependency graph as steps, inverse of every group's block:
+    plan_triangular)."""
 
     def __init__(self, T, lower, unit_diagonal, device):
         torch = require_cuda()
         p = plan_triangular(T, lower)
         self.n, self.lower = p["n"], bool(lower)
         self.nlevels, self.nsteps, self.nnz, self.ngroups = p["nlevels"], p["nsteps"], p["nnz"], p["ngroups"]
-        self.max_multi = p["max_multi"]
-        self.step_lo, self.step_mid, self.step_hi, self.step_kind = p["step_lo"], p["step_mid"], p["step_hi"], p["step_kind"]
-        self.launches = int((self.step_kind == 0).sum() + ((self.step_kind == 1) & (self.step_mid > self.step_lo)).sum()
-                            + ((self.step_kind == 1) & (self.step_hi > self.step_mid)).sum())
+        self.step_lo, self.step_hi, self.step_kind = p["step_lo"], p["step_hi"], p["step_kind"]
+        self.launches = int(self.nsteps)
+        self.group_levels = int((self.step_kind == 2).sum())
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
         self.rowptr, self.col, self.val = dev(p["rowptr"]), dev(p["col"]), dev(p["val"])
-        self.diag = None if unit_diagonal else dev(p["diag"])
+        # divisor per position: 1 inside groups (the division is in the block inverse); for a unit
+        # diagonal every divisor is 1 and the kernels skip the division altogether
+        self.diag = None if unit_diagonal else dev(p["diag_eff"])
         self.order_host, self.pos_host = p["order"], p["pos"]            # schedule order (host): X[p] = row order[p]
         self.split = dev(p["split"])
         self.grp_start, self.grp_rows = dev(p["grp_start"]), dev(p["grp_rows"])
-        ng = self.ngroups
-        gop = np.full(max(self.n, 1), -1, dtype=np.int32)              # group of the row at every order position
-        if ng:
-            gs, gr = p["grp_start"][:ng], p["grp_rows"][:ng]
-            gop[np.repeat(gs, gr) + (np.arange(int(gr.sum())) - np.repeat(np.cumsum(gr) - gr, gr))] = \
-                np.repeat(np.arange(ng, dtype=np.int32), gr)
-        self.grp_of_pos = dev(gop)
-        self.grp_start_host = np.ascontiguousarray(p["grp_start"][:max(ng, 1)], dtype=np.int64)
-        self.grp_csum_host = np.ascontiguousarray(np.concatenate([[0], np.cumsum(p["grp_rows"][:ng])]), dtype=np.int64)
-        self._scratch = {}
+        self.dinv_ptr, self.dinv = dev(p["dinv_ptr"]), dev(p["dinv"])
 
     def solve_inplace(self, X, m):
         """T X = X on the (n, ldx) device block with the m right-hand sides contiguous, rows in
         SCHEDULE order: X[p] belongs to row order_host[p] of T."""
-        import torch
         ldx = X.stride(0)
-        # one scratch (external sums + ticket counters) per stream: solves on different streams never share it
-        key = (ldx, X.device.index, torch.cuda.current_stream(X.device).cuda_stream)
-        if key not in self._scratch:
-            self._scratch[key] = torch.zeros(lib().rla_sptrsv_scratch_bytes(ldx, self.max_multi), dtype=torch.uint8,
-                                             device=X.device)
-        sc = self._scratch[key]
         check(lib().rla_sptrsv_solve_f64(self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
                                          None if self.diag is None else self.diag.data_ptr(),
-                                         self.split.data_ptr(), self.grp_start.data_ptr(),
-                                         self.grp_rows.data_ptr(), self.grp_of_pos.data_ptr(),
-                                         self.grp_start_host.ctypes.data, self.grp_csum_host.ctypes.data,
-                                         self.step_lo.ctypes.data, self.step_mid.ctypes.data,
-                                         self.step_hi.ctypes.data, self.step_kind.ctypes.data, self.nsteps,
-                                         self.max_multi, X.data_ptr(), int(m), ldx, sc.data_ptr(), sc.numel(),
+                                         self.split.data_ptr(), self.grp_start.data_ptr(), self.grp_rows.data_ptr(),
+                                         self.dinv_ptr.data_ptr(), self.dinv.data_ptr(),
+                                         self.step_lo.ctypes.data, self.step_hi.ctypes.data,
+                                         self.step_kind.ctypes.data, self.nsteps, X.data_ptr(), int(m), ldx,
                                          stream_ptr()), "rla_sptrsv_solve_f64")
         return X
 

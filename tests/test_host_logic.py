@@ -67,7 +67,8 @@ def test_new_entry_points_validate_arguments_without_gpu():
     happen on the host before any CUDA call."""
     import ctypes
     lib = rb.lib()
-    assert lib.rla_sptrsv_scratch_bytes(64, 256) >= 256 * 32 * 64 * 8
+    assert lib.rla_sptrsv_solve_f64(None, None, None, None, None, None, None, None, None, None, None, None, 3, None, 4, 3, None) == -1   # odd ldx
+    assert lib.rla_sptrsv_group_inverses_host(2, None, None, None, None, None, 0, None, None, None, None, None) == -1
     assert lib.rla_svd_jacobi_block_scratch_ints(256, 8, 30) == 30 + 32 + 8
     assert lib.rla_svd_jacobi_block_rows(1024, 256, 1) in (0, 2, 4, 8)          # 0 without a device
     # odd ldx / negative sizes / null pointers -> RLA_ERR_INVALID (-1), no device touched

@@ -17,38 +17,53 @@ def _fem(nx):
 
 
 def _replay(p, B, unit):
-    """What trsv_wide_kernel / trsv_groups_kernel compute, step by step, in schedule order:
-    X[q] is row order[q]; external column indices are positions, internal ones slots."""
+    """What the device kernels compute, step by step, in schedule order: X[q] is row order[q];
+    external column indices are positions, internal ones slots of the row's group.
+    kind 0 / 1: every row of the position range subtracts its external entries (and divides by its
+    effective diagonal: 1 inside groups); kind 2: x = Dinv y for every group of the range."""
     rowptr, col, val, order, split = p["rowptr"], p["col"], p["val"], p["order"], p["split"]
+    n = p["n"]
     X = B[order].copy()
-    done = np.zeros(p["n"], dtype=bool)
-    for lo, mid, hi, kind in zip(p["step_lo"], p["step_mid"], p["step_hi"], p["step_kind"]):
+    done = np.zeros(n, dtype=bool)           # final value available
+    summed = np.zeros(n, dtype=bool)         # external entries subtracted
+    in_group = np.zeros(n, dtype=bool)
+    for g in range(p["ngroups"]):
+        g0, nr = p["grp_start"][g], p["grp_rows"][g]
+        assert 2 <= nr <= 128 and not in_group[g0:g0 + nr].any()
+        in_group[g0:g0 + nr] = True
+    assert np.all(p["diag_eff"][in_group] == 1.0) and np.all(p["diag_eff"][~in_group] == p["diag"][~in_group])
+    resolved_groups = 0
+    for lo, hi, kind in zip(p["step_lo"], p["step_hi"], p["step_kind"]):
+        assert hi > lo and kind in (0, 1, 2)
         new = {}
-        if kind == 0:
+        if kind in (0, 1):
             for i in range(lo, hi):
-                e0, e1 = rowptr[i], rowptr[i + 1]
-                assert split[i] == e1 and np.all(done[col[e0:e1]])        # only rows of earlier steps
-                new[i] = (X[i] - val[e0:e1] @ X[col[e0:e1]]) / (1.0 if unit else p["diag"][i])
+                e0, sp_, e1 = rowptr[i], split[i], rowptr[i + 1]
+                assert np.all(done[col[e0:sp_]]) and not summed[i]         # external: earlier steps only
+                assert in_group[i] or sp_ == e1                            # single rows have no internal entries
+                new[i] = (X[i] - val[e0:sp_] @ X[col[e0:sp_]]) / (1.0 if unit else p["diag_eff"][i])
+                summed[i] = True
+            for i, v in new.items():
+                X[i] = v
+                done[i] = not in_group[i]
         else:
-            assert hi - lo >= 1 and mid - lo <= p["max_multi"]
+            assert lo == resolved_groups                                    # groups are resolved in order, once
             for g in range(lo, hi):
                 g0, nr = p["grp_start"][g], p["grp_rows"][g]
-                assert 1 <= nr <= 32 and (nr > 1) == (g < mid)
-                if g > lo:
-                    assert g0 == p["grp_start"][g - 1] + p["grp_rows"][g - 1]   # a step is contiguous in the order
-                xs = np.zeros((nr,) + X.shape[1:])
+                assert summed[g0:g0 + nr].all() and not done[g0:g0 + nr].any()
+                Dinv = p["dinv"][p["dinv_ptr"][g]:p["dinv_ptr"][g + 1]].reshape(nr, nr)
+                D = np.zeros((nr, nr))
                 for q in range(nr):
                     i = g0 + q
-                    e0, sp, e1 = rowptr[i], split[i], rowptr[i + 1]
-                    assert np.all(done[col[e0:sp]])                       # external: earlier steps only
-                    assert np.all(col[sp:e1] < q)                         # internal: earlier slots of the group
-                    acc = X[i] - val[e0:sp] @ X[col[e0:sp]] - val[sp:e1] @ xs[col[sp:e1]]
-                    xs[q] = acc / (1.0 if unit else p["diag"][i])
-                    new[i] = xs[q]
-        for i, v in new.items():                                          # a step only becomes visible at its end
-            X[i] = v
-            done[i] = True
-    assert done.all()
+                    sp_, e1 = split[i], rowptr[i + 1]
+                    assert np.all(col[sp_:e1] < q)                          # internal: earlier slots of the group
+                    D[q, col[sp_:e1]] = val[sp_:e1]
+                    D[q, q] = 1.0 if unit else p["diag"][i]
+                assert np.allclose(Dinv @ D, np.eye(nr), atol=1e-10) and np.all(np.triu(Dinv, 1) == 0)
+                X[g0:g0 + nr] = Dinv @ X[g0:g0 + nr]
+                done[g0:g0 + nr] = True
+            resolved_groups = hi
+    assert done.all() and resolved_groups == p["ngroups"]
     out = np.empty_like(X)
     out[order] = X
     return out
@@ -68,6 +83,27 @@ def test_plan_replay_matches_scipy(nx):
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-12
 
 
+def test_chain_groups_do_not_depend_on_unrelated_rows():
+    """A 384-row dependency chain next to 40 independent 3-row chains: the long chain is cut into three
+    groups of 128 whatever happens at the same levels elsewhere (round 1 cut bands of levels short
+    as soon as ANY connected component of the band outgrew a group)."""
+    n_chain, n_small = 384, 40
+    n = n_chain + 3 * n_small
+    rows, cols = [], []
+    for i in range(1, n_chain):
+        rows += [i] * min(i, 5); cols += list(range(max(0, i - 5), i))          # banded chain: each row needs the 5 before it
+    for c in range(n_small):
+        b = n_chain + 3 * c
+        rows += [b + 1, b + 2]; cols += [b, b + 1]
+    T = (sp.csr_matrix((np.full(len(rows), 0.3), (rows, cols)), shape=(n, n)) + 2.0 * sp.eye(n)).tocsr()
+    p = plan_triangular(T, True)
+    sizes = sorted(p["grp_rows"][:p["ngroups"]].tolist(), reverse=True)
+    assert sizes[:3] == [128, 128, 128] and sizes[3:] == [3] * n_small
+    assert int((p["step_kind"] == 2).sum()) == 3          # three group levels
+    B = np.random.RandomState(1).standard_normal((n, 2))
+    assert np.allclose(_replay(p, B, False), spsolve_triangular(T, B, lower=True))
+
+
 def test_plan_small_cases():
     # diagonal matrix: one level; strictly sequential chain: one group after another
     p = plan_triangular(sp.eye(5, format="csr") * 2.0, True)
@@ -75,8 +111,9 @@ def test_plan_small_cases():
     n = 70
     T = (sp.eye(n) + sp.diags([np.ones(n - 1)], [-1])).tocsr()
     p = plan_triangular(T, True)
-    assert p["nlevels"] == n and p["nsteps"] == 3 and list(p["step_kind"]) == [1, 1, 1]
-    assert list(p["grp_rows"][:p["ngroups"]]) == [32, 32, 6]
+    # one chain of 70 rows: ONE group; one external-sum step (nothing to subtract) and one resolve step
+    assert p["nlevels"] == n and list(p["step_kind"]) == [0, 2]
+    assert list(p["grp_rows"][:p["ngroups"]]) == [70]
     B = np.arange(n, dtype=float).reshape(-1, 1)
     assert np.allclose(_replay(p, B, True), spsolve_triangular(T, B, lower=True))
     with pytest.raises(Exception):

@@ -57,8 +57,8 @@ def run_c4(nx=1000, m=64, k=1000, hbm_peak=6549.8, with_cpu=True):
     res["host_splu_s"] = time.time() - t0
     lu = rinv._device_lu
     t0 = time.time(); fL, fU = lu._factors(False)[:2]; res["host_plan_s"] = time.time() - t0
-    res["L"] = {"nnz": fL.nnz, "levels": fL.nlevels, "launches": fL.nsteps, "groups": int((fL.step_kind == 1).sum())}
-    res["U"] = {"nnz": fU.nnz, "levels": fU.nlevels, "launches": fU.nsteps, "groups": int((fU.step_kind == 1).sum())}
+    res["L"] = {"nnz": fL.nnz, "row_levels": fL.nlevels, "launches": fL.nsteps, "group_levels": fL.group_levels, "groups": fL.ngroups}
+    res["U"] = {"nnz": fU.nnz, "row_levels": fU.nlevels, "launches": fU.nsteps, "group_levels": fU.group_levels, "groups": fU.ngroups}
     U = torch.randn(m, n, dtype=torch.float64, device="cuda")
     Uva = space.from_numpy(U)
     res["spmm_ms"] = timeit(lambda: ops_dev[0].apply(Uva))
