@@ -65,6 +65,32 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return done;
 }
+// cluster pairs: the Theta tile of a stage is written by the producers of BOTH CTAs of a pair
+// (each generates half of the rows into its own shared memory and pushes that slice to its
+// peer with a DSMEM bulk copy that signals the peer's full barrier through complete_tx).
+// Barrier operations on a peer use the default .release.cta form, as TMA-multicast pipelines
+// do: the explicit .cluster scope costs MEMBAR.ALL.GPU / CCTL.IVALL per stage (measured: the
+// pair ran 5 % slower than no pair at all).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void dsmem_push(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -79,6 +105,7 @@ __device__ __forceinline__ void lds_f64x2(uint32_t addr, double2 &v) {
 }
 struct GemmArgs {
     int64_t m, k, n;          // Y is m x k, reduction over n
+    int64_t kc0, kc1;         // sketch columns [kc0, kc1) handled by this launch
     int64_t kper;             // 16-wide k blocks per chunk
     int64_t nchunks;
     int mtiles, ntiles;       // tiles along m and along the sketch dimension
@@ -92,180 +119,234 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 // MODE 0: Theta explicit (second tensor map); 1: Philox normal; 2: Philox Rademacher
+// NG: 8-wide column groups per consumer warp (warp tile 64 x 8 NG; CTA tile BM x BN = 64 WM x 8 NG WN)
+// CL: CTAs per cluster along m (RNG modes): the pair works on the same Theta tile, each
+//     CTA's producers generate BN / CL of its rows per stage and store them into the shared
+//     memory of every CTA of the cluster (st.shared::cluster), so a Theta entry is generated
+//     once per CL * BM rows of U.  Measured (tools/micro/gemm_probe.cu): every instruction the
+//     producer warp of a sub-partition issues costs the DMMA pipe ~0.3 cycles, so the
+//     generator's instruction count is what separates this mode from the explicit one.
 //
 // Warp roles: warps 0..7 are DMMA consumers (2 per SM sub-partition, free-running: they
 // only meet through the per-stage full/empty mbarriers, so one warp's shared-memory
 // bubble is covered by the other's DMMAs); warps 8..11 are producers: lane 0 of warp 8
-// issues the TMA loads, and in the RNG modes all 128 producer threads generate the
-// [BN x 16] Theta tile of the stage (one sketch row each, four Philox blocks) straight
-// into the swizzled shared-memory layout the consumers read.
-template <int WM, int WN, int MODE>
+// issues the TMA loads, and in the RNG modes all 128 producer threads generate Theta
+// (one Philox block = four consecutive entries of a row per item) straight into the
+// swizzled shared-memory layout the consumers read.
+template <int WM, int WN, int NG, int MODE, int CL>
 __global__ void __launch_bounds__(GTHREADS + GPRODUCERS, 1)
 sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT, const GemmArgs a) {
-    constexpr int BM = WM * 64, BN = WN * 32;
+    constexpr int BM = WM * 64, BN = WN * NG * 8;
     static_assert(WM * WN == GWARPS, "8 consumer warps");
+    static_assert(MODE != 0 || CL == 1, "explicit Theta: no cluster");
     constexpr int A_BYTES = BM * GK * 8;
     constexpr int B_BYTES = BN * GK * 8;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TX_BYTES = (MODE == 0) ? STAGE_BYTES : A_BYTES;
+    constexpr int NPW = (MODE == 0) ? 1 : GPRODUCERS / 32;     // producer warps that do work
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[GSTAGES];
     __shared__ __align__(8) uint64_t empty_bar[GSTAGES];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // blockIdx.x = ntile + ntiles * (mtile + mtiles * chunk): CTAs sharing a U chunk are adjacent
-    int64_t b = blockIdx.x;
+    // blockIdx.x = rank + CL * (ntile + ntiles * (mgroup + mgroups * chunk)): the CTAs of a
+    // cluster are consecutive, CTAs sharing a U chunk are adjacent
+    const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0u;
+    int64_t b = blockIdx.x / CL;
     const int ntile = (int)(b % a.ntiles); b /= a.ntiles;
-    const int mtile = (int)(b % a.mtiles); b /= a.mtiles;
+    const int mgrp = a.mtiles / CL;
+    const int mtile = (int)(b % mgrp) * CL + (int)rank; b /= mgrp;
     const int64_t chunk = b;
     const int64_t kb0 = chunk * a.kper;
     const int64_t nk16 = (a.n + GK - 1) / GK;
     const int64_t kb1 = (kb0 + a.kper < nk16) ? kb0 + a.kper : nk16;
     const int iters = (int)(kb1 - kb0);
-    const int m0 = mtile * BM, n0 = ntile * BN;
+    const int m0 = mtile * BM, n0 = (int)a.kc0 + ntile * BN;
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < GSTAGES; ++s) {
-            mbar_init(&full_bar[s], MODE == 0 ? 1 : 1 + GPRODUCERS / 32);
-            mbar_init(&empty_bar[s], GWARPS);
+            mbar_init(&full_bar[s], MODE == 0 ? 1 : 1 + NPW);
+            mbar_init(&empty_bar[s], GWARPS * CL);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
 
     if (warp >= GWARPS) {
         // ------------------------------------------------------------ producers
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        const int p = tid - GTHREADS;                  // 0..127: row of the Theta tile
-        for (int it = 0; it < iters; ++it) {
-            const int s = it % GSTAGES;
-            if (it >= GSTAGES) mbar_wait(&empty_bar[s], ((it / GSTAGES) - 1) & 1);
-            unsigned char *st = smem + s * STAGE_BYTES;
-            if (p == 0) {
-                mbar_expect_tx(&full_bar[s], TX_BYTES);
-                const int x = (int)((kb0 + it) * GK);
-                tma_load_2d(st, &mapU, &full_bar[s], x, m0);
-                if (MODE == 0) tma_load_2d(st + A_BYTES, &mapT, &full_bar[s], x, n0);
+        if (warp < GWARPS + NPW) {
+            const int p = tid - GTHREADS;                  // 0..127
+            const int pw = warp - GWARPS;                  // producer warp
+            // RNG modes: warp pw owns RPW consecutive rows of this CTA's slice
+            // [rank * BN / CL, (rank + 1) * BN / CL) of the Theta tile; a thread's items of a stage
+            // are (row, quad) = (RPW pw + 8 j + lane / 4, lane & 3): one Philox block each
+            constexpr int ROWS_PER_CTA = BN / CL;
+            constexpr int NITEM = (ROWS_PER_CTA + 31) / 32;
+            constexpr int RPW = 8 * NITEM;
+            const int c = lane & 3;
+            const int wrow0 = (int)rank * ROWS_PER_CTA + RPW * pw;              // first row of this warp inside the tile
+            const int wrows = min(max(ROWS_PER_CTA - RPW * pw, 0), RPW);      // rows this warp owns (multiple of 8)
+            const uint32_t smem_b = smem_u32(smem) + A_BYTES;
+            uint32_t peer_b = 0, peer_full = 0;
+            if (CL > 1) {
+                peer_b = mapa_u32(smem_b, rank ^ 1u);
+                peer_full = mapa_u32(smem_u32(&full_bar[0]), rank ^ 1u);
             }
-            if (MODE != 0) {
-#pragma unroll 1
-                for (int r = p; r < BN; r += GPRODUCERS) {
-                    if (n0 + r < a.k) {
-                        const uint32_t trow = (uint32_t)(a.row0 + n0 + r);
-                        const uint64_t q0 = (uint64_t)(a.col0 + (kb0 + it) * GK) >> 2;
-                        unsigned char *rowp = st + A_BYTES + r * 128;
-                        const int sw = r & 7;
+            uint64_t q = ((uint64_t)(a.col0 + kb0 * GK) >> 2) + (uint64_t)c;
+            for (int it = 0; it < iters; ++it, q += GK / 4) {
+                const int s = it % GSTAGES;
+                if (it >= GSTAGES) mbar_wait(&empty_bar[s], ((it / GSTAGES) - 1) & 1);
+                unsigned char *st = smem + s * STAGE_BYTES;
+                if (p == 0) {
+                    mbar_expect_tx(&full_bar[s], TX_BYTES + (CL - 1) * ROWS_PER_CTA * 128);
+                    const int x = (int)((kb0 + it) * GK);
+                    tma_load_2d(st, &mapU, &full_bar[s], x, m0);
+                    if (MODE == 0) tma_load_2d(st + A_BYTES, &mapT, &full_bar[s], x, n0);
+                }
+                if (MODE != 0) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                    for (int j = 0; j < NITEM; ++j) {
+                        const int rl = 8 * j + (lane >> 2);
+                        const int r = wrow0 + rl;                                   // row inside the tile
+                        if (rl < wrows && n0 + r < a.kc1) {
                             double v[4];
-                            if (MODE == 1) theta4<0>(a.seed, trow, q0 + c, v);
-                            else theta4<1>(a.seed, trow, q0 + c, v);
-                            *reinterpret_cast<double2 *>(rowp + (((2 * c) ^ sw) << 4)) = make_double2(v[0], v[1]);
-                            *reinterpret_cast<double2 *>(rowp + (((2 * c + 1) ^ sw) << 4)) = make_double2(v[2], v[3]);
+                            if (MODE == 1) theta4<0>(a.seed, (uint32_t)(a.row0 + n0 + r), q, v);
+                            else theta4<1>(a.seed, (uint32_t)(a.row0 + n0 + r), q, v);
+                            unsigned char *rowp = st + A_BYTES + r * 128;
+                            *reinterpret_cast<double2 *>(rowp + (((2 * c) ^ (r & 7)) << 4)) = make_double2(v[0], v[1]);
+                            *reinterpret_cast<double2 *>(rowp + (((2 * c + 1) ^ (r & 7)) << 4)) = make_double2(v[2], v[3]);
                         }
                     }
+                    if (CL > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CL > 1 && wrows > 0) {
+                            const uint32_t off = (uint32_t)(s * STAGE_BYTES + wrow0 * 128);
+                            dsmem_push(peer_b + off, smem_b + off, (uint32_t)wrows * 128u, peer_full + (uint32_t)s * 8u);
+                        }
+                        mbar_arrive(&full_bar[s]);
+                    }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[s]);
             }
         }
-        return;
-    }
-
+    } else {
     // ---------------------------------------------------------------- consumers
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / WN, wn = warp % WN;
-    double acc[8][4][2];
+    double acc[8][NG][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < NG; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     // 8-wide column groups of this warp that fall inside the sketch (ragged k), row groups inside m
-    const int64_t ng64 = (a.k - (n0 + wn * 32) + 7) / 8;
-    const int ngroups = ng64 < 0 ? 0 : (ng64 > 4 ? 4 : (int)ng64);
+    const int64_t ng64 = (a.kc1 - (n0 + wn * NG * 8) + 7) / 8;
+    const int ngroups = ng64 < 0 ? 0 : (ng64 > NG ? NG : (int)ng64);
     const int64_t mg64 = (a.m - (m0 + wm * 64) + 7) / 8;
     const int mgroups = mg64 < 0 ? 0 : (mg64 > 8 ? 8 : (int)mg64);
 
-    // Fragments are held per 8-wide half of the 16-wide k block, double buffered: while the
-    // 64 DMMAs of one half issue, the 12 LDS.128 of the next half are in flight.  In half h
-    // a thread owns k = 4t + 2h + {0, 1} of every row: the 16-byte chunk 2t + h, XOR-swizzled
-    // with (row & 7) = g for every row this thread touches.
-    double2 a8[2][8], b8[2][4];
+    // empty barriers of every CTA of the cluster (lane r signals CTA r)
+    uint32_t empty_addr = smem_u32(&empty_bar[0]);
+    if (CL > 1) empty_addr = mapa_u32(empty_addr, (uint32_t)(lane < CL ? lane : 0));
+
+    // Fragments are held per 8-wide half of the 16-wide k block.  In half h a thread owns
+    // k = 4t + 2h + {0, 1} of every row: the 16-byte chunk 2t + h, XOR-swizzled with
+    // (row & 7) = g for every row this thread touches.  The B fragments (Theta, used by every
+    // row group) are double buffered; an A fragment is reloaded for the next half right after
+    // the 4 NG DMMAs of its pair of row groups, so only one set of A fragments is live
+    // (192 + 16 NG registers of tile state instead of 224 + ...: no spills at 232).
+    double2 a8[8], b8[2][NG];
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t row_off = (uint32_t)g * 128u;
     const uint32_t off0 = row_off + ((uint32_t)((2 * t) ^ g) << 4);
     const uint32_t off1 = row_off + ((uint32_t)((2 * t + 1) ^ g) << 4);
-    const uint32_t a_warp = (uint32_t)(wm * 64) * 128u, b_warp = (uint32_t)A_BYTES + (uint32_t)(wn * 32) * 128u;
-#define LOAD_FRAGS(BUF, STAGE, OFF)                                                              \
+    const uint32_t a_warp = smem_base + (uint32_t)(wm * 64) * 128u, b_warp = smem_base + (uint32_t)A_BYTES + (uint32_t)(wn * NG * 8) * 128u;
+#define LOAD_A(I, STAGE, OFF) lds_f64x2(a_warp + (OFF) + (STAGE) * STAGE_BYTES + (I) * 1024, a8[I])
+#define LOAD_B(BUF, STAGE, OFF)                                                                  \
     {                                                                                            \
-        const uint32_t sa_ = smem_base + (STAGE) * STAGE_BYTES + a_warp + (OFF);                 \
-        const uint32_t sb_ = smem_base + (STAGE) * STAGE_BYTES + b_warp + (OFF);                 \
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) lds_f64x2(sa_ + i * 1024, a8[BUF][i]);     \
-        _Pragma("unroll") for (int j = 0; j < 4; ++j) lds_f64x2(sb_ + j * 1024, b8[BUF][j]);     \
+        const uint32_t sb_ = b_warp + (OFF) + (STAGE) * STAGE_BYTES;                             \
+        _Pragma("unroll") for (int j = 0; j < NG; ++j) lds_f64x2(sb_ + j * 1024, b8[BUF][j]);    \
     }
-#define MMA_HALF(BUF, PRED)                                                                      \
+    // row groups I, I + 1 against the NG column groups: both k4 steps of the half; an
+    // accumulator is touched again after 2 NG DMMAs
+#define MMA_PAIR(I, BUF)                                                                         \
     {                                                                                            \
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                          \
-            if (!(PRED) || i < mgroups) {                                                        \
-                _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                  \
-                    if (!(PRED) || j < ngroups) dmma884(acc[i][j][0], acc[i][j][1], a8[BUF][i].x, b8[BUF][j].x); \
-                }                                                                                \
-            }                                                                                    \
-        }                                                                                        \
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                          \
-            if (!(PRED) || i < mgroups) {                                                        \
-                _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                  \
-                    if (!(PRED) || j < ngroups) dmma884(acc[i][j][0], acc[i][j][1], a8[BUF][i].y, b8[BUF][j].y); \
-                }                                                                                \
-            }                                                                                    \
-        }                                                                                        \
+        _Pragma("unroll") for (int ii = (I); ii < (I) + 2; ++ii)                                 \
+            _Pragma("unroll") for (int j = 0; j < NG; ++j)                                       \
+                dmma884(acc[ii][j][0], acc[ii][j][1], a8[ii].x, b8[BUF][j].x);                   \
+        _Pragma("unroll") for (int ii = (I); ii < (I) + 2; ++ii)                                 \
+            _Pragma("unroll") for (int j = 0; j < NG; ++j)                                       \
+                dmma884(acc[ii][j][0], acc[ii][j][1], a8[ii].y, b8[BUF][j].y);                   \
     }
-#define CONSUMER_LOOP(PRED)                                                                      \
-    for (int it = 0; it < iters; ++it) {                                                         \
-        const int s = it % GSTAGES;                                                              \
-        LOAD_FRAGS(1, s, off1);                                                                  \
-        const bool more = it + 1 < iters;                                                        \
-        const int sn = (it + 1) % GSTAGES;                                                       \
-        const uint32_t pn = ((it + 1) / GSTAGES) & 1;                                            \
-        uint32_t ready = 1;                                                                      \
-        if (more) ready = mbar_try_wait(&full_bar[sn], pn);   /* polled early, used after the DMMAs */ \
-        MMA_HALF(0, PRED);                                                                       \
-        if (more) {                                                                              \
-            while (!ready) ready = mbar_try_wait(&full_bar[sn], pn);                             \
-            LOAD_FRAGS(0, sn, off0);                                                             \
-        }                                                                                        \
-        MMA_HALF(1, PRED);                                                                       \
-        /* every shared-memory read of stage s has completed (its data fed the DMMAs above) */   \
+#define FULL_TRY(BAR, PAR) mbar_try_wait(BAR, PAR)
+#define RELEASE_STAGE(S)                                                                         \
+    {                                                                                            \
         __syncwarp();                                                                            \
-        if (lane == 0) mbar_arrive(&empty_bar[s]);                                               \
+        if (CL > 1) { if (lane < CL) mbar_arrive_remote(empty_addr + (uint32_t)(S) * 8u); }      \
+        else if (lane == 0) mbar_arrive(&empty_bar[S]);                                          \
     }
 
-    if (iters > 0) {
-        mbar_wait(&full_bar[0], 0);
-        LOAD_FRAGS(0, 0, off0);
-    }
-    // A warp with any row and column group inside the sketch runs the whole 64 x 32 warp tile
+    // A warp with any row and column group inside the sketch runs the whole warp tile
     // without predicates or branches between the DMMAs: rows beyond m are zero-filled by TMA
     // and columns beyond k are computed but never stored.  Warps entirely outside only keep
     // the pipeline barriers moving.
     if (mgroups > 0 && ngroups > 0) {
-        CONSUMER_LOOP(false)
+        if (iters > 0) {
+            while (!FULL_TRY(&full_bar[0], 0)) {}
+#pragma unroll
+            for (int i = 0; i < 8; ++i) LOAD_A(i, 0, off0);
+            LOAD_B(0, 0, off0);
+        }
+        // the ring is unrolled so that stage offsets and barrier addresses are immediates
+        uint32_t ph = 0;                                   // parity of the ring pass of iteration it0
+        for (int it0 = 0; it0 < iters; it0 += GSTAGES, ph ^= 1u) {
+#pragma unroll
+            for (int s = 0; s < GSTAGES; ++s) {
+                const int it = it0 + s;
+                if (it >= iters) break;
+                const bool more = it + 1 < iters;
+                const int sn = (s + 1) % GSTAGES;
+                const uint32_t pn = (s + 1 == GSTAGES) ? (ph ^ 1u) : ph;
+                LOAD_B(1, s, off1);
+                uint32_t ready = 1;
+                if (more) ready = FULL_TRY(&full_bar[sn], pn);   /* polled early, used after the DMMAs */
+#pragma unroll
+                for (int ip = 0; ip < 4; ++ip) {
+                    MMA_PAIR(2 * ip, 0);
+                    LOAD_A(2 * ip, s, off1);
+                    LOAD_A(2 * ip + 1, s, off1);
+                }
+                if (more) { while (!ready) ready = FULL_TRY(&full_bar[sn], pn); }
+                /* after the last iteration these loads fetch stale (harmless) data */
+                LOAD_B(0, sn, off0);
+#pragma unroll
+                for (int ip = 0; ip < 4; ++ip) {
+                    MMA_PAIR(2 * ip, 1);
+                    LOAD_A(2 * ip, sn, off0);
+                    LOAD_A(2 * ip + 1, sn, off0);
+                }
+                /* every shared-memory read of stage s was issued before the second half and has
+                   completed (its data fed the DMMAs above) */
+                RELEASE_STAGE(s);
+            }
+        }
     } else {
         for (int it = 0; it < iters; ++it) {
             const int s = it % GSTAGES;
-            if (it > 0) mbar_wait(&full_bar[s], (it / GSTAGES) & 1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            while (!FULL_TRY(&full_bar[s], (it / GSTAGES) & 1)) {}
+            RELEASE_STAGE(s);
         }
     }
-#undef CONSUMER_LOOP
-#undef LOAD_FRAGS
-#undef MMA_HALF
+#undef LOAD_A
+#undef LOAD_B
+#undef MMA_PAIR
+#undef FULL_TRY
+#undef RELEASE_STAGE
 
     // partial tile -> workspace [chunk][m][k]
     double *wsp = a.ws + chunk * a.m * a.k;
@@ -274,20 +355,26 @@ sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
         const int64_t row = m0 + wm * 64 + 8 * i + g;
         if (row >= a.m) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t col = n0 + wn * 32 + 8 * j + 2 * t;
-            if (col < a.k) wsp[row * a.k + col] = acc[i][j][0];
-            if (col + 1 < a.k) wsp[row * a.k + col + 1] = acc[i][j][1];
+        for (int j = 0; j < NG; ++j) {
+            const int64_t col = n0 + wn * NG * 8 + 8 * j + 2 * t;
+            if (col < a.kc1) wsp[row * a.k + col] = acc[i][j][0];
+            if (col + 1 < a.kc1) wsp[row * a.k + col + 1] = acc[i][j][1];
         }
     }
+    }
+    // no CTA of a cluster may exit while a peer can still store into its shared memory or
+    // signal its barriers
+    if (CL > 1) cluster_sync_all();
 }
 
-// y[c, i] = (accumulate ? y[c, i] : 0) + scale * sum_chunks ws[chunk][c][i]
-__global__ void gemm_reduce_kernel(const double *__restrict__ ws, int64_t nchunks, int64_t m, int64_t k,
-                                   double scale, double *__restrict__ y, int64_t ldy, int accumulate) {
+// y[c, i] = (accumulate ? y[c, i] : 0) + scale * sum_chunks ws[chunk][c][i]; columns below ksplit
+// were produced in nchunks0 partial sketches, the others in nchunks1
+__global__ void gemm_reduce_kernel(const double *__restrict__ ws, int64_t nchunks0, int64_t nchunks1, int64_t ksplit,
+                                   int64_t m, int64_t k, double scale, double *__restrict__ y, int64_t ldy, int accumulate) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= m * k) return;
     const int64_t row = idx / k, col = idx % k;
+    const int64_t nchunks = col < ksplit ? nchunks0 : nchunks1;
     double s = 0.0;
     for (int64_t c = 0; c < nchunks; ++c) s += ws[c * m * k + idx];
     double *dst = y + row * ldy + col;
@@ -376,60 +463,117 @@ static bool tma_ok(const double *p, int64_t ld) {
 }
 
 struct GemmPlan {
-    int wm, wn, bm, bn;
+    int wm, wn, ng, cl, bm, bn;
     int mtiles, ntiles;
     int64_t kper, nchunks;
 };
 
-static GemmPlan plan_gemm(int64_t m, int64_t k, int64_t n) {
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// plan of one range of kcols sketch columns; ng = 0: choose the column groups per warp
+// rng: Theta generated in the kernel (cluster pairs along m share the generation)
+static GemmPlan plan_range(int64_t m, int64_t kcols, int64_t n, bool rng, int ng) {
     GemmPlan p;
-    // CTA tile (wm*64) x (wn*32).  128 x 128 measured best for m > 64 (256 x 64 halves the
-    // Theta generation per flop but is ~2% slower); 64 x 256 for m <= 64
-    static int wm_env = -1;
-    if (wm_env < 0) { const char *e = getenv("RLA_GEMM_WM"); wm_env = e ? atoi(e) : 0; }
+    // CTA tile (wm*64) x (wn*8*ng).  128 x 128 measured best for m > 64; 64 x 256 for m <= 64
+    static const int wm_env = env_int("RLA_GEMM_WM", 0), cl_env = env_int("RLA_GEMM_CL", 0),
+                     waves_env = env_int("RLA_GEMM_WAVES", 24);
     if (wm_env == 1 || wm_env == 2 || wm_env == 4) p.wm = wm_env;
     else p.wm = m > 64 ? 2 : 1;
     p.wn = GWARPS / p.wm;
-    p.bm = p.wm * 64; p.bn = p.wn * 32;
+    p.bm = p.wm * 64;
+    p.ng = (p.wm == 2 && ng == 3) ? 3 : 4;
+    p.bn = p.wn * p.ng * 8;
     p.mtiles = (int)((m + p.bm - 1) / p.bm);
-    p.ntiles = (int)((k + p.bn - 1) / p.bn);
+    p.ntiles = (int)((kcols + p.bn - 1) / p.bn);
+    p.cl = (rng && p.wm == 2 && p.mtiles % 2 == 0) ? 2 : 1;
+    if (cl_env == 1) p.cl = 1;
     const int64_t nk16 = (n + GK - 1) / GK;
     const int64_t tiles = (int64_t)p.mtiles * p.ntiles;
-    static int waves_env = -1;
-    if (waves_env < 0) { const char *e = getenv("RLA_GEMM_WAVES"); waves_env = e ? atoi(e) : 8; }
     const int64_t sms = sm_count();
     const int64_t target = sms * waves_env;
-    // candidates around target / tiles; keep every chunk >= 32 k-blocks unless the problem is
-    // tiny, and pick the chunk count whose grid fills its last wave best (one CTA per SM)
+    // chunk counts up to target / tiles; keep every chunk >= 32 k-blocks unless the problem is
+    // tiny, and pick the count whose grid fills its last wave best (one CTA per SM), preferring
+    // fewer chunks (less workspace) among near-equal fills
     const int64_t cmax = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, nk16 / 32), (target + tiles - 1) / tiles));
-    const int64_t cmin = std::max<int64_t>(1, cmax / 2);
+    const int64_t cmin = std::max<int64_t>(1, cmax / 4);
     int64_t chunks = cmax;
     double best = -1.0;
-    for (int64_t c = cmax; c >= cmin; --c) {
+    for (int64_t c = cmin; c <= cmax; ++c) {
         const int64_t kper = (nk16 + c - 1) / c;
         const int64_t nc = (nk16 + kper - 1) / kper;
         const int64_t grid = nc * tiles;
         const int64_t waves = (grid + sms - 1) / sms;
         // useful work / occupied SM time (chunks are kper blocks long, the last may be shorter)
         const double eff = (double)nk16 * tiles / ((double)waves * sms * kper);
-        if (eff > best + 1e-9) { best = eff; chunks = c; }
+        if (eff > best + 2e-3) { best = eff; chunks = c; }
     }
     p.kper = (nk16 + chunks - 1) / chunks;
     p.nchunks = (nk16 + p.kper - 1) / p.kper;
     return p;
 }
 
-template <int WM, int WN, int MODE>
+// The sketch columns are covered by up to two launches: full 128-column tiles, then the
+// ragged rest with 96-column tiles when that wastes fewer columns (k = 2000: 15 x 128 + 80,
+// the 80 in one 96-wide tile, instead of 16 x 128 = 2048 computed columns).
+struct GemmRanges {
+    int count;
+    int64_t kc0[2], kc1[2];
+    GemmPlan plan[2];
+    int64_t max_chunks() const { return count == 2 ? std::max(plan[0].nchunks, plan[1].nchunks) : plan[0].nchunks; }
+};
+
+static GemmRanges plan_gemm(int64_t m, int64_t k, int64_t n, bool rng) {
+    GemmRanges r;
+    static const int split_env = env_int("RLA_GEMM_SPLIT", 1);
+    const GemmPlan whole = plan_range(m, k, n, rng, 4);
+    const int64_t kmain = k / whole.bn * whole.bn, ktail = k - kmain;
+    // split when the tail fits fewer 96-wide tiles' worth of computed columns than 128-wide ones
+    const bool split = split_env && whole.wm == 2 && kmain > 0 && ktail > 0 &&
+                       (ktail + 95) / 96 * 96 < (ktail + 127) / 128 * 128;
+    if (!split) {
+        r.count = 1; r.kc0[0] = 0; r.kc1[0] = k; r.plan[0] = whole;
+        return r;
+    }
+    r.count = 2;
+    r.kc0[0] = 0; r.kc1[0] = kmain; r.plan[0] = plan_range(m, kmain, n, rng, 4);
+    r.kc0[1] = kmain; r.kc1[1] = k; r.plan[1] = plan_range(m, ktail, n, rng, 3);
+    return r;
+}
+
+template <int WM, int WN, int NG, int MODE, int CL>
 static int launch_gemm(const CUtensorMap &mu, const CUtensorMap &mt, const GemmArgs &a, int64_t grid, cudaStream_t st) {
-    auto kern = sketch_gemm_kernel<WM, WN, MODE>;
-    constexpr int BM = WM * 64, BN = WN * 32;
+    auto kern = sketch_gemm_kernel<WM, WN, NG, MODE, CL>;
+    constexpr int BM = WM * 64, BN = WN * NG * 8;
     constexpr int stage = BM * GK * 8 + BN * GK * 8;
     const int smem = GSTAGES * stage + 1024;
     RLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(unsigned)grid, GTHREADS + GPRODUCERS, smem, st>>>(mu, mt, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(GTHREADS + GPRODUCERS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    RLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mu, mt, a));
     count_launch();
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;
+}
+
+template <int MODE>
+static int dispatch_gemm(const GemmPlan &p, const CUtensorMap &mu, const CUtensorMap &mt, const GemmArgs &a, int64_t grid,
+                         cudaStream_t st) {
+    constexpr int CLR = MODE == 0 ? 1 : 2;     // cluster pairs only when Theta is generated
+    if (p.wm == 4) return launch_gemm<4, 2, 4, MODE, 1>(mu, mt, a, grid, st);
+    if (p.wm == 1) return launch_gemm<1, 8, 4, MODE, 1>(mu, mt, a, grid, st);
+    if (p.ng == 3) return p.cl == 2 ? launch_gemm<2, 4, 3, MODE, CLR>(mu, mt, a, grid, st) : launch_gemm<2, 4, 3, MODE, 1>(mu, mt, a, grid, st);
+    return p.cl == 2 ? launch_gemm<2, 4, 4, MODE, CLR>(mu, mt, a, grid, st) : launch_gemm<2, 4, 4, MODE, 1>(mu, mt, a, grid, st);
 }
 
 // mode 0 explicit / 1 normal / 2 rademacher
@@ -437,36 +581,35 @@ static int sketch_gemm(int mode, const double *theta, int64_t ldt, uint64_t seed
                        int64_t col0, const double *u, int64_t m, int64_t ldu, int64_t k, int64_t n, double *y,
                        int64_t ldy, int accumulate, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (m == 0 || k == 0) return RLA_OK;
-    const GemmPlan p = plan_gemm(m, k, n);
-    const size_t need = (size_t)p.nchunks * m * k * sizeof(double);
+    const GemmRanges rg = plan_gemm(m, k, n, mode != 0);
+    const size_t need = (size_t)rg.max_chunks() * m * k * sizeof(double);
     if (ws_bytes < need) return fail(RLA_ERR_WORKSPACE, "sketch gemm: workspace %zu < %zu bytes", ws_bytes, need);
-    CUtensorMap mu, mt;
-    int rc = make_map(&mu, u, m, n, ldu, p.bm);
-    if (rc != RLA_OK) return rc;
-    if (mode == 0) {
-        rc = make_map(&mt, theta, k, n, ldt, p.bn);
+    for (int ri = 0; ri < rg.count; ++ri) {
+        const GemmPlan &p = rg.plan[ri];
+        CUtensorMap mu, mt;
+        int rc = make_map(&mu, u, m, n, ldu, p.bm);
         if (rc != RLA_OK) return rc;
-    } else {
-        mt = mu;
+        if (mode == 0) {
+            // rows [kc0, kc1) of Theta: the map starts at row 0, the kernel offsets by kc0
+            rc = make_map(&mt, theta, rg.kc1[ri], n, ldt, p.bn);
+            if (rc != RLA_OK) return rc;
+        } else {
+            mt = mu;
+        }
+        GemmArgs a;
+        a.m = m; a.k = k; a.n = n; a.kc0 = rg.kc0[ri]; a.kc1 = rg.kc1[ri];
+        a.kper = p.kper; a.nchunks = p.nchunks; a.mtiles = p.mtiles; a.ntiles = p.ntiles;
+        a.ws = static_cast<double *>(ws); a.seed = seed; a.row0 = row0; a.col0 = col0;
+        const int64_t grid = (int64_t)p.mtiles * p.ntiles * p.nchunks;
+        RLA_REQUIRE(grid < (int64_t(1) << 31), "sketch gemm: grid too large");
+        rc = mode == 0 ? dispatch_gemm<0>(p, mu, mt, a, grid, st)
+           : mode == 1 ? dispatch_gemm<1>(p, mu, mt, a, grid, st) : dispatch_gemm<2>(p, mu, mt, a, grid, st);
+        if (rc != RLA_OK) return rc;
     }
-    GemmArgs a;
-    a.m = m; a.k = k; a.n = n; a.kper = p.kper; a.nchunks = p.nchunks; a.mtiles = p.mtiles; a.ntiles = p.ntiles;
-    a.ws = static_cast<double *>(ws); a.seed = seed; a.row0 = row0; a.col0 = col0;
-    const int64_t grid = (int64_t)p.mtiles * p.ntiles * p.nchunks;
-    RLA_REQUIRE(grid < (int64_t(1) << 31), "sketch gemm: grid too large");
-    if (p.wm == 4) {
-        rc = mode == 0 ? launch_gemm<4, 2, 0>(mu, mt, a, grid, st)
-           : mode == 1 ? launch_gemm<4, 2, 1>(mu, mt, a, grid, st) : launch_gemm<4, 2, 2>(mu, mt, a, grid, st);
-    } else if (p.wm == 2) {
-        rc = mode == 0 ? launch_gemm<2, 4, 0>(mu, mt, a, grid, st)
-           : mode == 1 ? launch_gemm<2, 4, 1>(mu, mt, a, grid, st) : launch_gemm<2, 4, 2>(mu, mt, a, grid, st);
-    } else {
-        rc = mode == 0 ? launch_gemm<1, 8, 0>(mu, mt, a, grid, st)
-           : mode == 1 ? launch_gemm<1, 8, 1>(mu, mt, a, grid, st) : launch_gemm<1, 8, 2>(mu, mt, a, grid, st);
-    }
-    if (rc != RLA_OK) return rc;
     const int64_t tot = m * k;
-    gemm_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a.ws, p.nchunks, m, k, scale, y, ldy, accumulate);
+    gemm_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        static_cast<double *>(ws), rg.plan[0].nchunks, rg.count == 2 ? rg.plan[1].nchunks : 0, rg.kc1[0], m, k, scale, y, ldy,
+        accumulate);
     count_launch();
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;
@@ -530,8 +673,9 @@ extern "C" int rla_philox4x32_10_device(const uint32_t *in, int64_t count, uint3
 
 extern "C" size_t rla_gemm_workspace_bytes(int64_t m, int64_t k, int64_t n) {
     if (m <= 0 || k <= 0 || n <= 0) return 0;
-    const GemmPlan p = plan_gemm(m, k, n);
-    return (size_t)p.nchunks * m * k * sizeof(double);
+    // the larger of the two modes' plans (they differ only in the cluster width today)
+    const GemmRanges p = plan_gemm(m, k, n, true), q = plan_gemm(m, k, n, false);
+    return (size_t)std::max(p.max_chunks(), q.max_chunks()) * m * k * sizeof(double);
 }
 
 extern "C" int rla_gauss_apply_explicit_f64(const double *theta, int64_t k, int64_t n, int64_t ldt, const double *u,

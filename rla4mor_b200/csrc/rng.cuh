@@ -7,7 +7,7 @@
 // DMMA fragments need, in registers; rla_theta_materialize_f64 exports the same values
 // (same device function, hence bit-identical) for parity checks against the oracle.
 //
-//   kind 0: standard normal by Box-Muller in FP32 (MUFU lg2 / sin / cos), widened to FP64
+//   kind 0: standard normal by Box-Muller in FP32 (MUFU lg2 / sqrt / sin / cos), widened to FP64
 //   kind 1: Rademacher +-1 (one bit per entry)
 // The 1/sqrt(k) scale of the reference (rla/embeddings.py:269) is applied by the caller.
 #pragma once
@@ -38,13 +38,22 @@ __host__ __device__ __forceinline__ PhiloxOut philox4x32_10(uint32_t c0, uint32_
     return PhiloxOut{c0, c1, c2, c3};
 }
 
-// two standard normals from two 32-bit words (FP32 Box-Muller); deterministic on sm_100
+// two standard normals from two 32-bit words (FP32 Box-Muller on the special-function unit:
+// MUFU.LG2 / MUFU.SQRT / MUFU.COS / MUFU.SIN, 12 instructions per pair; the IEEE sqrtf and the
+// denormal-safe __log2f cost 12 more, and every instruction the generator issues is taken
+// from the DMMA warps of its sub-partition).  Deterministic on sm_100; the approximations are
+// hardware-defined, so (kind, n, k, seed) determines Theta bit for bit on this architecture only.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1) {
-    const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (a + 0.5) 2^-32, > 0
+    const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (a + 0.5) 2^-32, in (0, 1]
     const float ang = (float)(int32_t)b * 1.4629180792671596e-9f;                         // pi 2^-31 b, [-pi, pi)
-    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));                            // sqrt(-2 ln u1)
-    n0 = r * __cosf(ang);
-    n1 = r * __sinf(ang);
+    float l, r, c, s;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
+    const float t = -1.3862943611198906f * l;                                             // -2 ln u1 >= 0
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+    n0 = r * c;
+    n1 = r * s;
 }
 
 // the four entries Theta[row, 4*q .. 4*q+3]  (q = col / 4) as doubles, unscaled
