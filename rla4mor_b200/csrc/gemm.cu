@@ -473,22 +473,33 @@ static int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-// plan of one range of kcols sketch columns; ng = 0: choose the column groups per warp
+// CTA tile rows / 64 for an (m, n) block.  Measured on C2 shapes (m = 512, k = 2048, Theta
+// generated in the kernel): 256 x 64 tiles in cluster pairs 35.9 TFLOP/s (a Theta entry is
+// generated once per 512 rows of U), 128 x 128 in pairs 35.2, 256 x 64 alone 35.3, 128 x 128
+// alone 33.8; with Theta explicit 128 x 128 reaches 36.2.  Fewest padded rows first.
+static int choose_wm(int64_t m, bool rng) {
+    static const int wm_env = env_int("RLA_GEMM_WM", 0);
+    if (wm_env == 1 || wm_env == 2 || wm_env == 4) return wm_env;
+    if (m <= 64) return 1;
+    const int64_t pad2 = (m + 127) / 128 * 128, pad4 = (m + 255) / 256 * 256;
+    if (!rng || pad2 < pad4) return 2;
+    const bool pair4 = (pad4 / 256) % 2 == 0, pair2 = (pad2 / 128) % 2 == 0;
+    return (pair4 || !pair2) ? 4 : 2;
+}
+
+// plan of one range of kcols sketch columns with ng column groups per consumer warp
 // rng: Theta generated in the kernel (cluster pairs along m share the generation)
-static GemmPlan plan_range(int64_t m, int64_t kcols, int64_t n, bool rng, int ng) {
+static GemmPlan plan_range(int64_t m, int64_t kcols, int64_t n, bool rng, int ng, bool pairs) {
     GemmPlan p;
-    // CTA tile (wm*64) x (wn*8*ng).  128 x 128 measured best for m > 64; 64 x 256 for m <= 64
-    static const int wm_env = env_int("RLA_GEMM_WM", 0), cl_env = env_int("RLA_GEMM_CL", 0),
-                     waves_env = env_int("RLA_GEMM_WAVES", 24);
-    if (wm_env == 1 || wm_env == 2 || wm_env == 4) p.wm = wm_env;
-    else p.wm = m > 64 ? 2 : 1;
+    static const int cl_env = env_int("RLA_GEMM_CL", 0), waves_env = env_int("RLA_GEMM_WAVES", 24);
+    p.wm = choose_wm(m, rng);
     p.wn = GWARPS / p.wm;
     p.bm = p.wm * 64;
-    p.ng = (p.wm == 2 && ng == 3) ? 3 : 4;
+    p.ng = p.wm == 1 ? 4 : ng;
     p.bn = p.wn * p.ng * 8;
     p.mtiles = (int)((m + p.bm - 1) / p.bm);
     p.ntiles = (int)((kcols + p.bn - 1) / p.bn);
-    p.cl = (rng && p.wm == 2 && p.mtiles % 2 == 0) ? 2 : 1;
+    p.cl = (rng && pairs && p.wm >= 2 && p.mtiles % 2 == 0) ? 2 : 1;
     if (cl_env == 1) p.cl = 1;
     const int64_t nk16 = (n + GK - 1) / GK;
     const int64_t tiles = (int64_t)p.mtiles * p.ntiles;
@@ -515,9 +526,9 @@ static GemmPlan plan_range(int64_t m, int64_t kcols, int64_t n, bool rng, int ng
     return p;
 }
 
-// The sketch columns are covered by up to two launches: full 128-column tiles, then the
-// ragged rest with 96-column tiles when that wastes fewer columns (k = 2000: 15 x 128 + 80,
-// the 80 in one 96-wide tile, instead of 16 x 128 = 2048 computed columns).
+// The sketch columns are covered by up to two launches: full tiles (4 column groups per
+// warp), then the ragged rest with the narrowest tile (1..3 groups per warp) that holds it
+// (k = 2000 with 64-wide tiles: 31 x 64 + one 16-wide tile instead of 32 x 64 = 2048 computed columns).
 struct GemmRanges {
     int count;
     int64_t kc0[2], kc1[2];
@@ -528,18 +539,17 @@ struct GemmRanges {
 static GemmRanges plan_gemm(int64_t m, int64_t k, int64_t n, bool rng) {
     GemmRanges r;
     static const int split_env = env_int("RLA_GEMM_SPLIT", 1);
-    const GemmPlan whole = plan_range(m, k, n, rng, 4);
+    const GemmPlan whole = plan_range(m, k, n, rng, 4, true);
     const int64_t kmain = k / whole.bn * whole.bn, ktail = k - kmain;
-    // split when the tail fits fewer 96-wide tiles' worth of computed columns than 128-wide ones
-    const bool split = split_env && whole.wm == 2 && kmain > 0 && ktail > 0 &&
-                       (ktail + 95) / 96 * 96 < (ktail + 127) / 128 * 128;
+    const int ngt = (int)((ktail + whole.wn * 8 - 1) / (whole.wn * 8));        // groups per warp the tail needs
+    const bool split = split_env && whole.wm >= 2 && kmain > 0 && ktail > 0 && ngt < 4;
     if (!split) {
         r.count = 1; r.kc0[0] = 0; r.kc1[0] = k; r.plan[0] = whole;
         return r;
     }
     r.count = 2;
-    r.kc0[0] = 0; r.kc1[0] = kmain; r.plan[0] = plan_range(m, kmain, n, rng, 4);
-    r.kc0[1] = kmain; r.kc1[1] = k; r.plan[1] = plan_range(m, ktail, n, rng, 3);
+    r.kc0[0] = 0; r.kc1[0] = kmain; r.plan[0] = plan_range(m, kmain, n, rng, 4, true);
+    r.kc0[1] = kmain; r.kc1[1] = k; r.plan[1] = plan_range(m, ktail, n, rng, ngt, false);
     return r;
 }
 
@@ -570,9 +580,16 @@ template <int MODE>
 static int dispatch_gemm(const GemmPlan &p, const CUtensorMap &mu, const CUtensorMap &mt, const GemmArgs &a, int64_t grid,
                          cudaStream_t st) {
     constexpr int CLR = MODE == 0 ? 1 : 2;     // cluster pairs only when Theta is generated
-    if (p.wm == 4) return launch_gemm<4, 2, 4, MODE, 1>(mu, mt, a, grid, st);
     if (p.wm == 1) return launch_gemm<1, 8, 4, MODE, 1>(mu, mt, a, grid, st);
-    if (p.ng == 3) return p.cl == 2 ? launch_gemm<2, 4, 3, MODE, CLR>(mu, mt, a, grid, st) : launch_gemm<2, 4, 3, MODE, 1>(mu, mt, a, grid, st);
+    if (p.wm == 4) {
+        if (p.ng == 1) return launch_gemm<4, 2, 1, MODE, 1>(mu, mt, a, grid, st);
+        if (p.ng == 2) return launch_gemm<4, 2, 2, MODE, 1>(mu, mt, a, grid, st);
+        if (p.ng == 3) return launch_gemm<4, 2, 3, MODE, 1>(mu, mt, a, grid, st);
+        return p.cl == 2 ? launch_gemm<4, 2, 4, MODE, CLR>(mu, mt, a, grid, st) : launch_gemm<4, 2, 4, MODE, 1>(mu, mt, a, grid, st);
+    }
+    if (p.ng == 1) return launch_gemm<2, 4, 1, MODE, 1>(mu, mt, a, grid, st);
+    if (p.ng == 2) return launch_gemm<2, 4, 2, MODE, 1>(mu, mt, a, grid, st);
+    if (p.ng == 3) return launch_gemm<2, 4, 3, MODE, 1>(mu, mt, a, grid, st);
     return p.cl == 2 ? launch_gemm<2, 4, 4, MODE, CLR>(mu, mt, a, grid, st) : launch_gemm<2, 4, 4, MODE, 1>(mu, mt, a, grid, st);
 }
 
