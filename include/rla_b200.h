@@ -42,6 +42,9 @@ const char *rla_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench.py reports
  * the delta over its timed region as "gpu_launches") */
 unsigned long long rla_launch_count(void);
+/* Adds n to that counter: for kernels of this library replayed from a CUDA graph the caller captured
+ * (rla4mor_b200/factorization.py replays the launches of an LU solve that way). */
+void rla_launch_count_add(long long n);
 
 /* Pitched host<->device copy on `stream` (cudaMemcpy2DAsync): used to stream column slabs
  * of a row-major host block (pitches and width in BYTES; direction 0 = H2D, 1 = D2H). */

@@ -12,15 +12,24 @@ enforces that), and the product raises if its CUDA library is missing.
 
 Parity pin: the reference ships no golden vectors for this path (SURVEY.md
 section 8c).  The oracle is pinned instead against *outputs of the reference
-itself*: `oracle/make_golden.py` imports `/root/reference/rla/srht.py` by file
-path in the build container, runs `srht`, `fht_oop`, `fht_ip` on seeded inputs
-and commits the results under `tests/golden/`; `tests/test_oracle_golden.py`
-checks every oracle function against those fixtures.  The embedding classes in
-`rla/embeddings.py` cannot be imported (pyMOR is not installed and is not under
-/root/reference); their restatement is pinned by re-deriving each formula with
-plain NumPy inside `make_golden.py` from the cited reference lines -- that part
-is "parity unpinned by executable reference" and is flagged as such in
-DESIGN.md.
+itself*, generated in the build container and committed under `tests/golden/`:
+
+  * `oracle/make_golden.py` imports `/root/reference/rla/srht.py` by file path and
+    records `srht`, `fht_oop`, `fht_ip` on seeded inputs (`srht_reference.npz`,
+    `fht_reference.npz`);
+  * `oracle/make_golden_pymor.py` imports `/root/reference/rla/embeddings.py`,
+    `mor/sketched_reductor.py` and `utilities/*` UNMODIFIED on top of the tests-only pyMOR
+    stand-in `tests/_pymor_stub` (pyMOR is not in the image) and records every embedding
+    class (apply, adjoint, explicit matrices, blocks, seeds, dims, caching quirks) and the
+    whole SketchedReductor flow (galerkin, minres, empty ROM): `embeddings_reference.npz`,
+    `reductor_reference.npz`.
+
+`tests/test_oracle_golden.py` and `tests/test_reference_goldens_cpu.py` check every oracle
+function against those fixtures; the GPU tests compare the product with the same fixtures.
+What stays a restatement: pyMOR's own side of each call (`NumpyMatrixOperator.apply`,
+`gram_schmidt`, `project` / `expand` / `contract`), written in the stub from pyMOR 2023.1's
+documented semantics.  `embeddings_transcribed.npz` (round 1: the NumPy lines of
+`rla/embeddings.py` re-typed) is kept as a second, independent fixture.
 """
 from .srht_oracle import (  # noqa: F401
     rademacher_signs, sampling_indices, srht, fht_oop, fht_ip, srht_closed_form,

@@ -22,6 +22,7 @@ _SIGS = {
     "rla_version": (c_int, []),
     "rla_last_error": (c_char_p, []),
     "rla_launch_count": (ctypes.c_ulonglong, []),
+    "rla_launch_count_add": (None, [ctypes.c_longlong]),
     "rla_copy2d_async": (c_int, [_vp, c_size_t, _vp, c_size_t, c_size_t, c_size_t, c_int, _vp]),
     "rla_srht_plan_create": (c_int, [POINTER(c_void_p), _vp, c_int64, _vp, c_int64, c_int]),
     "rla_srht_plan_destroy": (None, [_vp]),

@@ -32,6 +32,8 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n
 
 extern "C" int rla_version(void) { return 100; }
 extern "C" unsigned long long rla_launch_count(void) { return __atomic_load_n(&rla::g_launches, __ATOMIC_RELAXED); }
+// kernels of this library replayed from a captured CUDA graph (the host-side launch calls do not run again)
+extern "C" void rla_launch_count_add(long long n) { rla::count_launch((int)n); }
 extern "C" const char *rla_last_error(void) { return rla::g_err; }
 
 // Pitched copy between host and device (cudaMemcpy2DAsync): the column slabs of a

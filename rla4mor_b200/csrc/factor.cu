@@ -665,8 +665,10 @@ extern "C" int rla_gram_schmidt_ws_f64(double *a, int64_t r, int64_t k, int64_t 
 extern "C" int rla_svd_jacobi_block_rows(int64_t k, int64_t m, int want_v) {
     if (k < 2 || (k & 1) || m < 4 || (want_v && (m & 1)) || !coop_ok()) return 0;
     const int sms = sm_count();
-    int bmax = 8;
-    if (const char *env = getenv("RLA_JACOBI_B")) bmax = std::max(2, std::min(8, atoi(env)));   // development
+    // without the accumulated rotations a row is half as long: 16 rows per block (16 warps per CTA,
+    // half as many block rounds) pay off; with them 8 measured best
+    int bmax = want_v ? 8 : 16;
+    if (const char *env = getenv("RLA_JACOBI_B")) bmax = std::max(2, std::min(16, atoi(env)));   // development
     for (int B = bmax; B >= 2; B >>= 1) {
         const size_t smem = (size_t)2 * B * (size_t)((k + (want_v ? m : 0) + 3) & ~int64_t(1)) * sizeof(double);
         const int64_t nblk = (m + B - 1) / B;
@@ -701,7 +703,8 @@ extern "C" int rla_svd_jacobi_block_f64(double *a, int64_t k, int64_t m, int64_t
     unsigned long long timeout_ns = 5000000000ull;
     void *args[] = {&a, &k, &lda, &V, &m, &sched_dev, &rounds, &tol, &max_sweeps, &counters, &s, &info, &blkflag, &bar,
                     &timeout_ns};
-    const void *fn = B == 8 ? (const void *)jacobi_block_kernel<8>
+    const void *fn = B == 16 ? (const void *)jacobi_block_kernel<16>
+                   : B == 8 ? (const void *)jacobi_block_kernel<8>
                    : B == 4 ? (const void *)jacobi_block_kernel<4> : (const void *)jacobi_block_kernel<2>;
     RLA_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RLA_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(npairs), dim3(32 * B), args, smem, st));

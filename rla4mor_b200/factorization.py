@@ -10,6 +10,7 @@ triangular solves of `slu.solve(V.T).T` (:118-132) over the whole block of vecto
 and constructor arguments as the reference.  Real matrices only.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -143,6 +144,11 @@ class SparseLU:
         self._perm_c = np.ascontiguousarray(factorization.perm_c, dtype=np.int64)
         self._fwd = None
         self._adj = None
+        # the few hundred launches of the two triangular solves are replayed as ONE CUDA graph per
+        # (direction, number of right-hand sides): the launches of a solve are 20-50 us each, so the
+        # gaps between dependent launches are a measurable part of it
+        self.use_graph = os.environ.get("RLA_SPTRSV_GRAPH", "1") != "0"
+        self._graph = None                                               # (key, X1, X2, CUDAGraph)
 
     def _factors(self, adjoint):
         """(first factor, second factor, perm_in, map_mid, perm_out): the block goes in with
@@ -182,15 +188,43 @@ class SparseLU:
             return out
         first, second, p_in, p_mid, p_out = self._factors(adjoint)
         ldx = m + (m & 1)
-        with torch.cuda.device(B.device):
-            X1 = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
-            X2 = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
-            check(lib().rla_sptrsv_transpose_in_f64(B.data_ptr(), m, self.n, B.stride(0), p_in.data_ptr(),
-                                                    X1.data_ptr(), ldx, stream_ptr()), "rla_sptrsv_transpose_in_f64")
+
+        def solves(X1, X2):
             first.solve_inplace(X1, m)
             check(lib().rla_sptrsv_permute_rows_f64(X1.data_ptr(), p_mid.data_ptr(), X2.data_ptr(), self.n, ldx,
                                                     stream_ptr()), "rla_sptrsv_permute_rows_f64")
             second.solve_inplace(X2, m)
+
+        with torch.cuda.device(B.device):
+            key = (bool(adjoint), m)
+            graph = None
+            if self.use_graph and self._graph is not None and self._graph[0] == key:
+                _, X1, X2, graph = self._graph
+            else:
+                X1 = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
+                X2 = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
+            check(lib().rla_sptrsv_transpose_in_f64(B.data_ptr(), m, self.n, B.stride(0), p_in.data_ptr(),
+                                                    X1.data_ptr(), ldx, stream_ptr()), "rla_sptrsv_transpose_in_f64")
+            if graph is not None:
+                graph.replay()
+                lib().rla_launch_count_add(first.launches + second.launches + 1)
+            else:
+                solves(X1, X2)
+                if self.use_graph:
+                    # this call ran eagerly (and warmed everything up); the next one with the same
+                    # shape replays the capture on the same two buffers
+                    self._graph = None
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        torch.cuda.current_stream().synchronize()
+                        n0 = lib().rla_launch_count()
+                        with torch.cuda.graph(g):                        # records the launches, runs nothing
+                            solves(X1, X2)
+                        lib().rla_launch_count_add(-int(lib().rla_launch_count() - n0))   # recorded, not run
+                        self._graph = (key, X1, X2, g)
+                    except Exception:                                    # capture unsupported: stay eager
+                        self.use_graph = False
+                        self._graph = None
             check(lib().rla_sptrsv_transpose_out_f64(X2.data_ptr(), m, self.n, ldx, p_out.data_ptr(),
                                                      out.data_ptr(), out.stride(0), stream_ptr()),
                   "rla_sptrsv_transpose_out_f64")

@@ -41,7 +41,7 @@ def thin_qr(S):
     return ops.gram_schmidt(S)
 
 
-def sketch_svd(S, want_v=True, precondition=None, qr=None):
+def sketch_svd(S, want_v=True, precondition=None, qr=None, T=None, w_from=None):
     """SVD of the k x m sketch held as the row block S (m, k): returns (U_rows (m, k), s (m,),
     W (m, m) or None) with S = W^T diag(s) U_rows, singular values descending
     (reductor_ops.svd_jacobi's convention).
@@ -49,7 +49,14 @@ def sketch_svd(S, want_v=True, precondition=None, qr=None):
     For k >= 2m the Jacobi iteration runs on the m x m triangular factor instead of the m x k
     sketch (QR preconditioning): S = R^T Q (Gram-Schmidt), R = W^T diag(s) Z (block Jacobi on the
     rows of R, length m), S = Z^T diag(s) (W Q).  Rows four times shorter at BASELINE configs[4]
-    and fewer sweeps."""
+    and fewer sweeps.
+
+    w_from: how the rotations W come out of the Jacobi iteration on R.  "accumulate": the kernel
+    applies every rotation to an identity as well (rows twice as long).  "solve": only the rows
+    of R are rotated (W R = diag(s) Z) and W = diag(s) Z R^-1 afterwards with T = R^-1, which the
+    reductor needs anyway (mor/sketched_reductor.py:95) -- the error of W grows with cond(R), so
+    this is the default (None) only when max|r_ii| / min|r_ii| < 1e4 and no row was removed (the
+    choice LAPACK's xGEJSV makes for its right factor)."""
     m, k = S.shape
     if precondition is None:
         precondition = k >= 2 * m and m >= 16
@@ -57,12 +64,24 @@ def sketch_svd(S, want_v=True, precondition=None, qr=None):
         return ops.svd_jacobi(S, want_v=want_v)
     Q, R = ops.gram_schmidt(S) if qr is None else qr    # S = R^T Q, R (m', m) with m' <= m kept rows
     mk = R.shape[0]
+    if w_from is None:
+        w_from = "accumulate"
+        if mk == m:
+            d = torch.diagonal(R).abs()
+            if float((d.max() / d.min()).item()) < 1e4:
+                w_from = "solve"
     # Jacobi on the ROWS OF R (Gram matrix R R^T, one QR-iteration step closer to diagonal than
     # S S^T = R^T R -- this is what makes the QR a preconditioner): W R = diag(s) Z, hence
     # S = R^T Q = Z^T diag(s) (W Q): left factor Z, right factor W Q.
     M = torch.zeros((mk, m + (m & 1)), dtype=torch.float64, device=S.device)
     M[:, :m] = R
-    Z, s, W = ops.svd_jacobi(M, want_v=True)            # rows of Z: normalised rotated rows of R
+    if w_from == "solve" and mk == m:
+        Z, s, _ = ops.svd_jacobi(M, want_v=False)       # rows of Z: normalised rotated rows of R
+        if T is None:
+            T = ops.pinv_R(R)
+        W = ops.gemm_nn(Z[:, :m] * s.unsqueeze(1), T)   # (diag(s) Z) R^-1
+    else:
+        Z, s, W = ops.svd_jacobi(M, want_v=True)
     Urows = ops.gemm_nn(W, Q)                           # (m', m') @ (m', k)
     Zm = Z[:, :m]
     if mk < m:                                          # rank-deficient: pad with zero singular values
@@ -80,6 +99,6 @@ def sketched_range_finder(U_local, n, k, seed=0, kind="srht", rank=0, world=1, g
         reducer.check_status()                          # thin_qr has synchronised already: this read is free
     out = {"sketch": S, "Q": Q, "R": R, "T": ops.pinv_R(R)}
     if svd:
-        Urows, s, W = sketch_svd(S, want_v=True, qr=(Q, R))
+        Urows, s, W = sketch_svd(S, want_v=True, qr=(Q, R), T=out["T"] if R.shape[0] == R.shape[1] else None)
         out.update(s=s, W=W, Urows=Urows)
     return out

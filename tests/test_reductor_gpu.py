@@ -143,6 +143,28 @@ def test_sketch_svd_qr_preconditioned(rb):
         assert rel_fro(Un @ Un.T, np.eye(r_num)) < 1e-6
 
 
+def test_sketch_svd_w_from_triangular_inverse(rb):
+    """Well-conditioned R: only the rows of R are rotated (16 rows per block) and W = diag(s) Z R^-1;
+    same factorisation as with accumulated rotations."""
+    from rla4mor_b200.rangefinder import sketch_svd
+    rs = np.random.RandomState(8)
+    for m, k in ((64, 512), (96, 200), (256, 1024)):
+        S = rs.standard_normal((m, k))
+        s_ref = np.linalg.svd(S, compute_uv=False)
+        got = {}
+        for mode in ("solve", "accumulate", None):
+            U, s, W = sketch_svd(_dev(S), want_v=True, precondition=True, w_from=mode)
+            assert np.max(np.abs(s.cpu().numpy() - s_ref)) / s_ref[0] < 1e-13
+            assert rel_fro(((W.T * s) @ U).cpu().numpy(), S) < 1e-12
+            assert rel_fro((W @ W.T).cpu().numpy(), np.eye(m)) < 1e-11
+            assert rel_fro((U @ U.T).cpu().numpy(), np.eye(m)) < 1e-11
+            got[mode] = (U.cpu().numpy(), W.cpu().numpy())
+        # singular vectors agree up to sign (distinct singular values)
+        for a, b in zip(got["solve"], got["accumulate"]):
+            sg = np.sign(np.sum(got["solve"][0] * got["accumulate"][0], axis=1))
+            assert rel_fro(a * sg[:, None], b) < 1e-8
+
+
 def test_pinv_R_triangular_inverse(rb):
     from rla4mor_b200 import reductor_ops as ops
     for r in (1, 5, 64, 257):
