@@ -665,9 +665,9 @@ extern "C" int rla_gram_schmidt_ws_f64(double *a, int64_t r, int64_t k, int64_t 
 extern "C" int rla_svd_jacobi_block_rows(int64_t k, int64_t m, int want_v) {
     if (k < 2 || (k & 1) || m < 4 || (want_v && (m & 1)) || !coop_ok()) return 0;
     const int sms = sm_count();
-    // without the accumulated rotations a row is half as long: 16 rows per block (16 warps per CTA,
-    // half as many block rounds) pay off; with them 8 measured best
-    int bmax = want_v ? 8 : 16;
+    // 8 rows per block measured best with and without the accumulated rotations (256 x 256 factor:
+    // 5.3 / 4.3 ms at B = 8, 7.0 / 5.5 at 16, 5.7 / 4.7 at 4)
+    int bmax = 8;
     if (const char *env = getenv("RLA_JACOBI_B")) bmax = std::max(2, std::min(16, atoi(env)));   // development
     for (int B = bmax; B >= 2; B >>= 1) {
         const size_t smem = (size_t)2 * B * (size_t)((k + (want_v ? m : 0) + 3) & ~int64_t(1)) * sizeof(double);

@@ -201,29 +201,34 @@ trsv_rows_cta_kernel(const TrsvArgs a, int64_t lo) {
     }
 }
 
-// kind 2: one CTA per group and chunk of right-hand sides.  The rows of the group hold
+// kind 2: P CTAs per group and chunk of right-hand sides.  The rows of the group hold
 // y = b - (external sums); x = Dinv y with the inverse of the group's triangular block (row-major
 // nrows x nrows at dinv + dinv_ptr[g], lower triangle).  y is staged in shared memory (lanes =
-// pairs of right-hand sides); warp w owns rows w, w + 16, ...: the entries of a row of Dinv come in
-// with one coalesced load per 32 and are broadcast by shuffles.
+// pairs of right-hand sides); row r belongs to CTA r % P, warp (r / P) % 16 of it.  The entries
+// of a row of Dinv come in with one coalesced load per 32 (zero beyond the diagonal) and are
+// broadcast by shuffles; a 32-entry piece is fully unrolled over four independent accumulator
+// pairs, so neither the shuffle nor the FP64 latency is on the critical path (the round-2a
+// kernel walked `cnt` entries with one accumulator: 32 us for ONE group, and a 2-D FEM factor
+// has ~150 group levels of one to a few groups each).  P = 4 when a step has few groups: the
+// step then lasts as long as a quarter of the chain's rows.
+template <int P>
 __global__ void __launch_bounds__(32 * TRSV_WARPS, 2)
 trsv_resolve_kernel(double *__restrict__ X, int64_t ldx, const int64_t *__restrict__ grp_start,
                     const int32_t *__restrict__ grp_rows, const int64_t *__restrict__ dinv_ptr,
                     const double *__restrict__ dinv, int64_t g_first) {
-    extern __shared__ __align__(16) double2 ys[];      // [nrows][32]
+    extern __shared__ __align__(16) double2 ys[];      // [TRSV_GROUP][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t gid = g_first + blockIdx.x;
+    const int64_t gid = g_first + blockIdx.x / P;
+    const int part = blockIdx.x % P;
     const int nrows = grp_rows[gid];
     const int64_t g0 = grp_start[gid];
     const double *Dg = dinv + dinv_ptr[gid];
     const int64_t c = (int64_t)blockIdx.y * TRSV_RHS + 2 * lane;
     const bool live = c < ldx;
-    for (int q = warp; q < nrows; q += TRSV_WARPS)
-        ys[q * 32 + lane] = live ? ldcg2(X + (g0 + q) * ldx + c) : make_double2(0.0, 0.0);
-    __syncthreads();
-    // Warp w owns rows w, w + 16, ..., longest first.  The (up to four) 32-entry pieces of a row of Dinv
-    // are fetched in one go, and the next row's pieces while this row is multiplied: the loads are
-    // never on the critical path.
+    // rows up to the last 32-entry piece any row of this group touches; beyond nrows: zeros
+    const int npad = (nrows + 31) & ~31;
+    for (int q = warp; q < npad; q += TRSV_WARPS)
+        ys[q * 32 + lane] = (live && q < nrows) ? ldcg2(X + (g0 + q) * ldx + c) : make_double2(0.0, 0.0);
     constexpr int NP = TRSV_GROUP / 32;
     auto fetch = [&](int r, double (&dv)[NP]) {
 #pragma unroll
@@ -232,25 +237,34 @@ trsv_resolve_kernel(double *__restrict__ X, int64_t ldx, const int64_t *__restri
             dv[k] = (r >= 0 && q <= r) ? __ldg(Dg + (int64_t)r * nrows + q) : 0.0;
         }
     };
-    int r = nrows - 1 >= warp ? warp + ((nrows - 1 - warp) / TRSV_WARPS) * TRSV_WARPS : -1;
+    // this warp's rows: r = part + P * (warp + 16 j), longest first
+    const int stride = P * TRSV_WARPS;
+    const int rfirst = part + P * warp;
+    int r = nrows - 1 >= rfirst ? rfirst + ((nrows - 1 - rfirst) / stride) * stride : -1;
     double dv[NP], dn[NP];
     fetch(r, dv);
-    for (; r >= 0; r -= TRSV_WARPS) {
-        fetch(r - TRSV_WARPS, dn);
-        double2 acc = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (; r >= 0; r -= stride) {
+        fetch(r - stride, dn);
+        double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
-            const int q0 = 32 * k;
-            if (q0 <= r) {
-                const int cnt = min(32, r + 1 - q0);
-                for (int u = 0; u < cnt; ++u) {
-                    const double v = __shfl_sync(0xffffffffu, dv[k], u);
-                    const double2 y = ys[(q0 + u) * 32 + lane];
-                    acc.x = fma(v, y.x, acc.x); acc.y = fma(v, y.y, acc.y);
+            if (32 * k <= r) {
+                const double2 *yk = ys + (32 * k) * 32 + lane;
+#pragma unroll
+                for (int u = 0; u < 32; u += 4) {
+                    const double v0 = __shfl_sync(0xffffffffu, dv[k], u), v1 = __shfl_sync(0xffffffffu, dv[k], u + 1);
+                    const double v2 = __shfl_sync(0xffffffffu, dv[k], u + 2), v3 = __shfl_sync(0xffffffffu, dv[k], u + 3);
+                    const double2 y0 = yk[u * 32], y1 = yk[(u + 1) * 32], y2 = yk[(u + 2) * 32], y3 = yk[(u + 3) * 32];
+                    a0.x = fma(v0, y0.x, a0.x); a0.y = fma(v0, y0.y, a0.y);
+                    a1.x = fma(v1, y1.x, a1.x); a1.y = fma(v1, y1.y, a1.y);
+                    a2.x = fma(v2, y2.x, a2.x); a2.y = fma(v2, y2.y, a2.y);
+                    a3.x = fma(v3, y3.x, a3.x); a3.y = fma(v3, y3.y, a3.y);
                 }
             }
         }
-        if (live) *reinterpret_cast<double2 *>(X + (g0 + r) * ldx + c) = acc;
+        if (live) *reinterpret_cast<double2 *>(X + (g0 + r) * ldx + c) =
+            make_double2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
 #pragma unroll
         for (int k = 0; k < NP; ++k) dv[k] = dn[k];
     }
@@ -555,7 +569,8 @@ extern "C" int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *co
     static bool attr_set = false;
     const int resolve_smem = TRSV_GROUP * 32 * (int)sizeof(double2);
     if (!attr_set) {
-        RLA_CUDA_CHECK(cudaFuncSetAttribute(trsv_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, resolve_smem));
+        RLA_CUDA_CHECK(cudaFuncSetAttribute(trsv_resolve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, resolve_smem));
+        RLA_CUDA_CHECK(cudaFuncSetAttribute(trsv_resolve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, resolve_smem));
         attr_set = true;
     }
     for (int64_t s = 0; s < nsteps; ++s) {
@@ -572,9 +587,16 @@ extern "C" int rla_sptrsv_solve_f64(const int64_t *rowptr_dev, const int32_t *co
         } else if (step_kind[s] == 2) {
             RLA_REQUIRE(grp_start_dev && grp_rows_dev && dinv_ptr_dev && dinv_dev && cnt < (int64_t(1) << 31),
                         "rla_sptrsv_solve_f64: group arrays missing");
-            dim3 grid((unsigned)cnt, chunks);
-            trsv_resolve_kernel<<<grid, 32 * TRSV_WARPS, resolve_smem, st>>>(x_dev, ldx, grp_start_dev, grp_rows_dev,
-                                                                            dinv_ptr_dev, dinv_dev, step_lo[s]);
+            // few groups in the step: four CTAs per group (a quarter of the chain's rows each)
+            if (cnt * chunks * 4 <= 2 * (int64_t)sm_count()) {
+                dim3 grid((unsigned)cnt * 4, chunks);
+                trsv_resolve_kernel<4><<<grid, 32 * TRSV_WARPS, resolve_smem, st>>>(x_dev, ldx, grp_start_dev, grp_rows_dev,
+                                                                                   dinv_ptr_dev, dinv_dev, step_lo[s]);
+            } else {
+                dim3 grid((unsigned)cnt, chunks);
+                trsv_resolve_kernel<1><<<grid, 32 * TRSV_WARPS, resolve_smem, st>>>(x_dev, ldx, grp_start_dev, grp_rows_dev,
+                                                                                   dinv_ptr_dev, dinv_dev, step_lo[s]);
+            }
         } else {
             return fail(RLA_ERR_INVALID, "rla_sptrsv_solve_f64: unknown step kind %d", step_kind[s]);
         }

@@ -148,7 +148,7 @@ class SparseLU:
         # (direction, number of right-hand sides): the launches of a solve are 20-50 us each, so the
         # gaps between dependent launches are a measurable part of it
         self.use_graph = os.environ.get("RLA_SPTRSV_GRAPH", "1") != "0"
-        self._graph = None                                               # (key, X1, X2, CUDAGraph)
+        self._graphs = {}                                                # (adjoint, m) -> (X1, X2, CUDAGraph), a few shapes
 
     def _factors(self, adjoint):
         """(first factor, second factor, perm_in, map_mid, perm_out): the block goes in with
@@ -198,8 +198,8 @@ class SparseLU:
         with torch.cuda.device(B.device):
             key = (bool(adjoint), m)
             graph = None
-            if self.use_graph and self._graph is not None and self._graph[0] == key:
-                _, X1, X2, graph = self._graph
+            if self.use_graph and key in self._graphs:
+                X1, X2, graph = self._graphs[key]
             else:
                 X1 = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
                 X2 = torch.empty((self.n, ldx), dtype=torch.float64, device=B.device)
@@ -213,7 +213,6 @@ class SparseLU:
                 if self.use_graph:
                     # this call ran eagerly (and warmed everything up); the next one with the same
                     # shape replays the capture on the same two buffers
-                    self._graph = None
                     try:
                         g = torch.cuda.CUDAGraph()
                         torch.cuda.current_stream().synchronize()
@@ -221,10 +220,14 @@ class SparseLU:
                         with torch.cuda.graph(g):                        # records the launches, runs nothing
                             solves(X1, X2)
                         lib().rla_launch_count_add(-int(lib().rla_launch_count() - n0))   # recorded, not run
-                        self._graph = (key, X1, X2, g)
+                        # extend_basis alternates between m right-hand sides (the images A_q U) and one
+                        # (the right-hand side of the model): keep a few shapes, oldest out first
+                        while len(self._graphs) >= 4:
+                            self._graphs.pop(next(iter(self._graphs)))
+                        self._graphs[key] = (X1, X2, g)
                     except Exception:                                    # capture unsupported: stay eager
                         self.use_graph = False
-                        self._graph = None
+                        self._graphs = {}
             check(lib().rla_sptrsv_transpose_out_f64(X2.data_ptr(), m, self.n, ldx, p_out.data_ptr(),
                                                      out.data_ptr(), out.stride(0), stream_ptr()),
                   "rla_sptrsv_transpose_out_f64")
