@@ -165,6 +165,20 @@ int rla_embed_apply_rng_f64(uint64_t seed, int kind, double scale,
                             const double *u_dev, int64_t m, int64_t ldu,
                             double *y_dev, int64_t ldy, int accumulate,
                             void *ws_dev, size_t ws_bytes, void *stream);
+/* The same for a FLOAT32 block (the optional FP32 path of north_star; tolerance 1e-5 relative
+ * Frobenius) on the generation-5 tensor cores: tcgen05.mma kind::tf32 with FP32 accumulators in
+ * TMEM that are flushed into FP64 every 64 terms, the block split into two TF32 parts (two MMAs
+ * per step).  Theta must be exact in TF32: kind 1 (Rademacher) or kind 2 (the normals of kind 0
+ * rounded to TF32; rla_embed_apply_rng_f64 / rla_theta_materialize_f64 accept kind 2 too, so
+ * Theta is the same matrix for both dtypes).  y is FLOAT64 (the reference's `Theta @ U.T` with a
+ * float64 Theta returns float64, rla/embeddings.py:250-254).  col0 must be a multiple of 32,
+ * u_dev 16-byte aligned, ldu a multiple of 4.  ws_dev: rla_gemm32_workspace_bytes(m, k_blk, n). */
+size_t rla_gemm32_workspace_bytes(int64_t m, int64_t k, int64_t n);
+int rla_embed_apply_rng_f32(uint64_t seed, int kind, double scale,
+                            int64_t row0, int64_t k_blk, int64_t col0, int64_t n,
+                            const float *u_dev, int64_t m, int64_t ldu,
+                            double *y_dev, int64_t ldy, int accumulate,
+                            void *ws_dev, size_t ws_bytes, void *stream);
 /* Export what the on-the-fly generator produces (parity tooling; replaces
  * get_random_matrix / _get_random_block, rla/embeddings.py:87-100, 452-461). */
 int rla_theta_materialize_f64(uint64_t seed, int kind, double scale,

@@ -46,6 +46,9 @@ _SIGS = {
                                              _vp, c_size_t, _vp]),
     "rla_embed_apply_rng_f64": (c_int, [c_uint64, c_int, c_double, c_int64, c_int64, c_int64, c_int64, _vp, c_int64,
                                         c_int64, _vp, c_int64, c_int, _vp, c_size_t, _vp]),
+    "rla_gemm32_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rla_embed_apply_rng_f32": (c_int, [c_uint64, c_int, c_double, c_int64, c_int64, c_int64, c_int64, _vp, c_int64,
+                                        c_int64, _vp, c_int64, c_int, _vp, c_size_t, _vp]),
     "rla_theta_materialize_f64": (c_int, [c_uint64, c_int, c_double, c_int64, c_int64, c_int64, c_int64, _vp, c_int64, _vp]),
     "rla_gemm_nn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rla_gemm_nn_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, c_int64, c_int64, _vp, c_int64, _vp, c_size_t, _vp]),

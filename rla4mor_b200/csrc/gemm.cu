@@ -118,7 +118,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// MODE 0: Theta explicit (second tensor map); 1: Philox normal; 2: Philox Rademacher
+// MODE 0: Theta explicit (second tensor map); 1: Philox normal; 2: Philox Rademacher; 3: Philox normal rounded to TF32
 // NG: 8-wide column groups per consumer warp (warp tile 64 x 8 NG; CTA tile BM x BN = 64 WM x 8 NG WN)
 // CL: CTAs per cluster along m (RNG modes): the pair works on the same Theta tile, each
 //     CTA's producers generate BN / CL of its rows per stage and store them into the shared
@@ -214,8 +214,7 @@ sketch_gemm_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
                         const int r = wrow0 + rl;                                   // row inside the tile
                         if (rl < wrows && n0 + r < a.kc1) {
                             double v[4];
-                            if (MODE == 1) theta4<0>(a.seed, (uint32_t)(a.row0 + n0 + r), q, v);
-                            else theta4<1>(a.seed, (uint32_t)(a.row0 + n0 + r), q, v);
+                            theta4<MODE - 1>(a.seed, (uint32_t)(a.row0 + n0 + r), q, v);   // MODE 1, 2, 3 = kind 0, 1, 2
                             unsigned char *rowp = st + A_BYTES + r * 128;
                             *reinterpret_cast<double2 *>(rowp + (((2 * c) ^ (r & 7)) << 4)) = make_double2(v[0], v[1]);
                             *reinterpret_cast<double2 *>(rowp + (((2 * c + 1) ^ (r & 7)) << 4)) = make_double2(v[2], v[3]);
@@ -620,7 +619,8 @@ static int sketch_gemm(int mode, const double *theta, int64_t ldt, uint64_t seed
         const int64_t grid = (int64_t)p.mtiles * p.ntiles * p.nchunks;
         RLA_REQUIRE(grid < (int64_t(1) << 31), "sketch gemm: grid too large");
         rc = mode == 0 ? dispatch_gemm<0>(p, mu, mt, a, grid, st)
-           : mode == 1 ? dispatch_gemm<1>(p, mu, mt, a, grid, st) : dispatch_gemm<2>(p, mu, mt, a, grid, st);
+           : mode == 1 ? dispatch_gemm<1>(p, mu, mt, a, grid, st)
+           : mode == 2 ? dispatch_gemm<2>(p, mu, mt, a, grid, st) : dispatch_gemm<3>(p, mu, mt, a, grid, st);
         if (rc != RLA_OK) return rc;
     }
     const int64_t tot = m * k;
@@ -716,7 +716,7 @@ extern "C" int rla_gauss_apply_explicit_f64(const double *theta, int64_t k, int6
 extern "C" int rla_embed_apply_rng_f64(uint64_t seed, int kind, double scale, int64_t row0, int64_t k_blk,
                                        int64_t col0, int64_t n, const double *u, int64_t m, int64_t ldu, double *y,
                                        int64_t ldy, int accumulate, void *ws, size_t ws_bytes, void *stream) {
-    RLA_REQUIRE(kind == 0 || kind == 1, "rla_embed_apply_rng_f64: kind must be 0 (normal) or 1 (rademacher)");
+    RLA_REQUIRE(kind >= 0 && kind <= 2, "rla_embed_apply_rng_f64: kind must be 0 (normal), 1 (rademacher) or 2 (normal rounded to TF32)");
     RLA_REQUIRE(k_blk >= 0 && n >= 1 && m >= 0 && ldu >= n && ldy >= k_blk && row0 >= 0 && col0 >= 0,
                 "rla_embed_apply_rng_f64: bad sizes");
     RLA_REQUIRE(col0 % 16 == 0, "rla_embed_apply_rng_f64: col0 must be a multiple of 16");
@@ -724,13 +724,13 @@ extern "C" int rla_embed_apply_rng_f64(uint64_t seed, int kind, double scale, in
     if (m == 0 || k_blk == 0) return RLA_OK;
     RLA_REQUIRE(u && y && ws, "rla_embed_apply_rng_f64: null pointer");
     RLA_REQUIRE(tma_ok(u, ldu), "rla_embed_apply_rng_f64: u must be 16-byte aligned with an even leading dimension");
-    return sketch_gemm(kind == 0 ? 1 : 2, nullptr, 0, seed, scale, row0, col0, u, m, ldu, k_blk, n, y, ldy,
+    return sketch_gemm(kind + 1, nullptr, 0, seed, scale, row0, col0, u, m, ldu, k_blk, n, y, ldy,
                        accumulate, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int rla_theta_materialize_f64(uint64_t seed, int kind, double scale, int64_t row0, int64_t rows,
                                          int64_t col0, int64_t cols, double *out, int64_t ldo, void *stream) {
-    RLA_REQUIRE(kind == 0 || kind == 1, "rla_theta_materialize_f64: kind must be 0 or 1");
+    RLA_REQUIRE(kind >= 0 && kind <= 2, "rla_theta_materialize_f64: kind must be 0, 1 or 2");
     RLA_REQUIRE(rows >= 0 && cols >= 0 && row0 >= 0 && col0 >= 0 && ldo >= cols, "rla_theta_materialize_f64: bad sizes");
     if (rows == 0 || cols == 0) return RLA_OK;
     RLA_REQUIRE(out, "rla_theta_materialize_f64: null pointer");
@@ -738,7 +738,8 @@ extern "C" int rla_theta_materialize_f64(uint64_t seed, int kind, double scale, 
     const int64_t tot = rows * nq;
     const unsigned grid = (unsigned)((tot + 255) / 256);
     if (kind == 0) theta_materialize_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, scale, row0, rows, col0, cols, out, ldo);
-    else theta_materialize_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, scale, row0, rows, col0, cols, out, ldo);
+    else if (kind == 1) theta_materialize_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, scale, row0, rows, col0, cols, out, ldo);
+    else theta_materialize_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, scale, row0, rows, col0, cols, out, ldo);
     count_launch();
     RLA_CUDA_CHECK(cudaGetLastError());
     return RLA_OK;

@@ -9,6 +9,11 @@
 //
 //   kind 0: standard normal by Box-Muller in FP32 (MUFU lg2 / sqrt / sin / cos), widened to FP64
 //   kind 1: Rademacher +-1 (one bit per entry)
+//   kind 2: the normals of kind 0 rounded to TF32 (10 explicit mantissa bits, round to nearest):
+//           every entry is exactly representable as an operand of the generation-5 tensor cores
+//           (tcgen05.mma kind::tf32), which the float32 path of gemm32.cu relies on; FP64 blocks
+//           sketched with kind 2 use the same rounded values, so Theta does not depend on the
+//           dtype of the block
 // The 1/sqrt(k) scale of the reference (rla/embeddings.py:269) is applied by the caller.
 #pragma once
 #include <stdint.h>
@@ -56,15 +61,23 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, fl
     n1 = r * s;
 }
 
-// the four entries Theta[row, 4*q .. 4*q+3]  (q = col / 4) as doubles, unscaled
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// the four entries Theta[row, 4*q .. 4*q+3]  (q = col / 4) as floats, unscaled
 template <int KIND>
-__device__ __forceinline__ void theta4(uint64_t seed, uint32_t row, uint64_t q, double (&out)[4]) {
-    if (KIND == 0) {
+__device__ __forceinline__ void theta4f(uint64_t seed, uint32_t row, uint64_t q, float (&out)[4]) {
+    if (KIND == 0 || KIND == 2) {
         const PhiloxOut p = philox4x32_10((uint32_t)q, row, (uint32_t)(q >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
-        float n0, n1, n2, n3;
-        box_muller(p.x, p.y, n0, n1);
-        box_muller(p.z, p.w, n2, n3);
-        out[0] = (double)n0; out[1] = (double)n1; out[2] = (double)n2; out[3] = (double)n3;
+        box_muller(p.x, p.y, out[0], out[1]);
+        box_muller(p.z, p.w, out[2], out[3]);
+        if (KIND == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = round_tf32(out[j]);
+        }
     } else {
         // 128 sign bits per Philox block: block index q / 32, bits 4*(q%32) .. +3
         const uint64_t blk = q >> 5;
@@ -74,8 +87,17 @@ __device__ __forceinline__ void theta4(uint64_t seed, uint32_t row, uint64_t q, 
         const uint32_t word = wsel == 0 ? p.x : (wsel == 1 ? p.y : (wsel == 2 ? p.z : p.w));
         const uint32_t bits = word >> (4 * (sel & 7));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) out[j] = ((bits >> j) & 1u) ? -1.0 : 1.0;
+        for (int j = 0; j < 4; ++j) out[j] = ((bits >> j) & 1u) ? -1.0f : 1.0f;
     }
+}
+
+// ... and as doubles (the FP64 kernels)
+template <int KIND>
+__device__ __forceinline__ void theta4(uint64_t seed, uint32_t row, uint64_t q, double (&out)[4]) {
+    float f[4];
+    theta4f<KIND>(seed, row, q, f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = (double)f[j];
 }
 
 }  // namespace rla

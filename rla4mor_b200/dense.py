@@ -12,6 +12,7 @@ from ._lib import check, lib, stream_ptr
 
 KIND_NORMAL = 0
 KIND_RADEMACHER = 1
+KIND_NORMAL_TF32 = 2      # the normals of kind 0 rounded to TF32: exact operands of tcgen05.mma kind::tf32
 
 def _workspace(nbytes, device):
     """Scratch for one call, taken from torch's caching allocator: it is tied to the current
@@ -66,9 +67,41 @@ def gauss_apply_explicit(theta, u, out=None):
     return out
 
 
+def _tma_friendly_f32(x):
+    """float32 rows for TMA: 16-byte aligned base, row stride a multiple of 4 elements."""
+    if x.data_ptr() % 16 == 0 and _ld(x) % 4 == 0:
+        return x
+    m, n = x.shape
+    buf = torch.zeros((m, (n + 3) // 4 * 4), dtype=x.dtype, device=x.device)
+    buf[:, :n] = x
+    return buf[:, :n]
+
+
 def embed_apply_rng(seed, kind, scale, k, u, row0=0, col0=0, out=None, accumulate=False):
     """Sketch u (m, n) with rows [row0, row0 + k) and columns [col0, col0 + n) of the
-    virtual matrix scale * g(seed, row, col); the matrix is never materialised."""
+    virtual matrix scale * g(seed, row, col); the matrix is never materialised.
+
+    float64 blocks run on the FP64 tensor pipe (csrc/gemm.cu).  float32 blocks with a Theta that
+    is exact in TF32 (KIND_RADEMACHER, KIND_NORMAL_TF32) run on the generation-5 tensor cores
+    (csrc/gemm32.cu: tcgen05 kind::tf32, two-part split of the block, FP64 accumulation of the
+    64-term partial sums); the sketch comes back as float64 either way."""
+    if u.dtype == torch.float32 and kind in (KIND_RADEMACHER, KIND_NORMAL_TF32) and col0 % 32 == 0:
+        u = _tma_friendly_f32(_rows(u))
+        m, n = u.shape
+        if out is None:
+            assert not accumulate
+            out = torch.empty((m, k), dtype=torch.float64, device=u.device)
+        if m == 0 or k == 0:
+            return out
+        with torch.cuda.device(u.device):
+            ws = _workspace(lib().rla_gemm32_workspace_bytes(m, k, n), u.device)
+            check(lib().rla_embed_apply_rng_f32(int(seed) & (2 ** 64 - 1), int(kind), float(scale), int(row0), int(k),
+                                                int(col0), n, u.data_ptr(), m, _ld(u), out.data_ptr(), out.stride(0),
+                                                1 if accumulate else 0, ws.data_ptr(), ws.numel(), stream_ptr()),
+                  "rla_embed_apply_rng_f32")
+        return out
+    if u.dtype == torch.float32:
+        u = u.to(torch.float64)
     u = _tma_friendly(_rows(u))
     assert u.dtype == torch.float64
     m, n = u.shape
