@@ -15,18 +15,19 @@
 //   * the FP32 accumulators in TMEM are flushed into FP64 registers every 64 terms.
 //
 // One CTA per SM, 128 x 128 tile of Y over one chunk of n (split-n as in gemm.cu: partial
-// tiles to a workspace, summed in chunk order by the reduce kernel), 16 warps:
+// tiles to a workspace, summed in chunk order by the reduce kernel), 20 warps:
 //   warps 0..7   flush: tcgen05.ld of the finished accumulator buffer, FP64 accumulate (64 per thread)
-//   warps 8..13  producers: generate the 128 x 32 Theta tile of the stage (Philox + Box-Muller,
+//   warps 8..17  producers: generate the 128 x 32 Theta tile of the stage (Philox + Box-Muller,
 //                rng.cuh) into the 128-byte-swizzled K-major layout; split the U tile TMA delivered
-//   warp 14      TMA: U tile of the stage (cp.async.bulk.tensor, 128-byte swizzle, zero fill)
-//   warp 15      MMA: one thread issues tcgen05.mma.kind::tf32 (M = N = 128, K = 8), two per k-step,
+//   warp 18      TMA: U tile of the stage (cp.async.bulk.tensor, 128-byte swizzle, zero fill)
+//   warp 19      MMA: one thread issues tcgen05.mma.kind::tf32 (M = N = 128, K = 8), two per k-step,
 //                tcgen05.commit releases the stage / hands the accumulator buffer to the flush warps
-// Registers: setmaxnreg moves registers inside the pool the CTA got at launch (512 threads x 128):
-// 8 flush warps at 184 + 8 small warps at 40 = 57 344 <= 65 536, and per SM sub-partition (warp w
-// lives on w % 4) 2 x 184 + 2 x 40 warps.  (A first version with 18 warps was launched with 96
-// registers per thread -- five warps on two sub-partitions -- and its pool of 55 296 could never
-// satisfy the increase: the flush warps waited for ever.)
+// Registers: setmaxnreg moves registers inside the pool the CTA got at launch (640 threads x 96 =
+// 61 440; five warps per SM sub-partition cap the launch at 96): 8 flush warps at 176 + 12 small
+// warps at 40 = 60 416, and per sub-partition (warp w lives on w % 4) 2 x 176 + 3 x 40 warps.
+// (A first version asked for more than its pool held: the flush warps waited for ever.)
+// The kernel is bound by the generator (1024 Philox blocks per stage against 512 cycles of MMA):
+// hence ten producer warps.
 // Two accumulator buffers in TMEM (2 x 128 columns): MMAs of chunk c + 1 run while chunk c is flushed.
 #include "common.cuh"
 #include "rng.cuh"
@@ -40,7 +41,7 @@ namespace rla {
 constexpr int TK = 32;                 // floats per row per stage (128 bytes = swizzle span)
 constexpr int TSTAGES = 4;
 constexpr int TBM = 128, TBN = 128;
-constexpr int TFLUSH = 8, TPROD = 6;   // warps
+constexpr int TFLUSH = 8, TPROD = 10;  // warps
 constexpr int TTHREADS = (TFLUSH + TPROD + 2) * 32;
 constexpr int TCHUNK = 2;              // stages per accumulator chunk: 64 terms in FP32, then FP64
 constexpr int T_TILE_BYTES = TBM * TK * 4;            // 16 KB
@@ -89,6 +90,28 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
+// the same arrive on the barrier at this offset in BOTH CTAs of a pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t t_mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void t_dsmem_push(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t t_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void t_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -102,7 +125,12 @@ struct Gemm32Args {
     int64_t row0, col0;       // offsets of this block inside the virtual Theta
 };
 
-template <int KIND>
+// CL = 2: the CTAs of a cluster pair work on the same Theta tile (same sketch rows, neighbouring
+// row tiles of U); each generates half of its rows and pushes them into the peer's tile with DSMEM
+// bulk copies that signal the peer's full barrier (complete_tx), and a stage is released on BOTH
+// CTAs by each MMA warp (multicast commit): the generator, which bounds this kernel, runs once
+// per 256 rows of U.
+template <int KIND, int CL>
 __global__ void __launch_bounds__(TTHREADS, 1)
 sketch_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapU, const Gemm32Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -111,9 +139,12 @@ sketch_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapU, const Gemm32Ar
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int64_t b = blockIdx.x;
+    // blockIdx.x = rank + CL * (ntile + ntiles * (mgroup + mgroups * chunk))
+    const uint32_t rank = (CL > 1) ? t_ctarank() : 0u;
+    int64_t b = blockIdx.x / CL;
     const int ntile = (int)(b % a.ntiles); b /= a.ntiles;
-    const int mtile = (int)(b % a.mtiles); b /= a.mtiles;
+    const int mgrp = a.mtiles / CL;
+    const int mtile = (int)(b % mgrp) * CL + (int)rank; b /= mgrp;
     const int64_t chunk = b;
     const int64_t kb0 = chunk * a.kper;
     const int64_t nk32 = (a.n + TK - 1) / TK;
@@ -125,8 +156,8 @@ sketch_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapU, const Gemm32Ar
 #pragma unroll
         for (int s = 0; s < TSTAGES; ++s) {
             t_mbar_init(&full_a[s], 1);
-            t_mbar_init(&full[s], TPROD);
-            t_mbar_init(&empty[s], 1);
+            t_mbar_init(&full[s], TPROD + (CL > 1 ? 1 : 0));       // + the expect_tx of the peer's half of Theta
+            t_mbar_init(&empty[s], CL);                            // the MMA warps of every CTA of the pair
         }
         t_mbar_init(&tmem_full[0], 1); t_mbar_init(&tmem_full[1], 1);
         t_mbar_init(&tmem_empty[0], TFLUSH); t_mbar_init(&tmem_empty[1], TFLUSH);
@@ -138,13 +169,13 @@ sketch_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapU, const Gemm32Ar
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) t_cluster_sync(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp < TFLUSH) {
         // ------------------------------------------------------------ flush warps
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
         const int q = warp & 3, h = warp >> 2;            // TMEM lane quarter (= warp % 4), column half
         double acc[64];
 #pragma unroll
@@ -194,24 +225,49 @@ sketch_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapU, const Gemm32Ar
     } else if (warp < TFLUSH + TPROD) {
         // ------------------------------------------------------------ producers
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        const int p = tid - TFLUSH * 32;                   // 0..191
+        const int p = tid - TFLUSH * 32;
+        const int pw = warp - TFLUSH;                      // producer warp
         constexpr int NPT = TPROD * 32;                    // producer threads: a multiple of 8
-        // Theta tile: 128 rows x 8 chunks of four floats = 1024 items; item = p + NPT j is chunk
-        // c = p & 7 of row item >> 3
+        // Theta tile: 128 rows x 8 chunks of four floats; this CTA generates ROWS = 128 / CL of them
+        // (rows [rank * ROWS, + ROWS)): item = p + NPT j is chunk c = p & 7 of row item >> 3 of that
+        // slice, so warp pw owns the 4 rows 4 pw + (NPT / 8) j .. + 3 per j: 512 contiguous bytes
+        constexpr int ROWS = TBN / CL;
+        constexpr int NJ = (ROWS * 8 + NPT - 1) / NPT;
         const int c = p & 7;
+        uint32_t peer_b = 0, peer_full = 0;
+        if (CL > 1) {
+            peer_b = t_mapa(s32(smem) + 2 * T_TILE_BYTES, rank ^ 1u);
+            peer_full = t_mapa(s32(&full[0]), rank ^ 1u);
+        }
         uint64_t qv = ((uint64_t)(a.col0 + kb0 * TK) >> 2) + (uint64_t)c;
         for (int it = 0; it < iters; ++it, qv += TK / 4) {
             const int s = it % TSTAGES;
             if (it >= TSTAGES) t_mbar_wait(&empty[s], (uint32_t)((it / TSTAGES) - 1) & 1u);
             unsigned char *st = smem + s * T_STAGE_BYTES;
+            if (CL > 1 && p == 0) t_mbar_expect_tx(&full[s], (CL - 1) * ROWS * 128);
 #pragma unroll
-            for (int j = 0; j < (TBN * 8 + NPT - 1) / NPT; ++j) {
-                const int r = (p + NPT * j) >> 3;
-                if (r < TBN && n0 + r < a.k) {
+            for (int j = 0; j < NJ; ++j) {
+                const int rl = (p + NPT * j) >> 3;                                  // row inside the slice
+                const int r = (int)rank * ROWS + rl;                                // row inside the tile
+                if (rl < ROWS && n0 + r < a.k) {
                     float f[4];
                     theta4f<KIND>(a.seed, (uint32_t)(a.row0 + n0 + r), qv, f);
                     *reinterpret_cast<float4 *>(st + 2 * T_TILE_BYTES + r * 128 + ((c ^ (r & 7)) << 4)) =
                         make_float4(f[0], f[1], f[2], f[3]);
+                }
+            }
+            if (CL > 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int rl0 = 4 * pw + (NPT / 8) * j;                     // first of this warp's 4 rows
+                        if (rl0 < ROWS) {
+                            const uint32_t off = (uint32_t)(s * T_STAGE_BYTES + ((int)rank * ROWS + rl0) * 128);
+                            t_dsmem_push(peer_b + off, s32(smem) + 2 * T_TILE_BYTES + off, 512u, peer_full + (uint32_t)s * 8u);
+                        }
+                    }
                 }
             }
             // split the U tile: raw stays (the tensor core truncates it to its TF32 high part),
@@ -271,13 +327,14 @@ sketch_gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapU, const Gemm32Ar
                     umma_tf32(d, da, db, idesc, (first && k == 0) ? 0u : 1u);
                     umma_tf32(d, dl, db, idesc, 1u);
                 }
-                umma_commit(&empty[s]);                                  // stage free when these MMAs are done
+                if (CL > 1) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);   // stage free when these MMAs are done
                 if ((it % TCHUNK) == TCHUNK - 1 || it == iters - 1) umma_commit(&tmem_full[buf]);
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    // no CTA of a pair may exit while its peer can still push into its shared memory or signal its barriers
+    if (CL > 1) t_cluster_sync(); else __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T_TMEM_COLS) : "memory");
     }
@@ -383,13 +440,23 @@ extern "C" int rla_embed_apply_rng_f32(uint64_t seed, int kind, double scale, in
     const int64_t grid = (int64_t)p.mtiles * p.ntiles * p.nchunks;
     RLA_REQUIRE(grid < (int64_t(1) << 31), "rla_embed_apply_rng_f32: grid too large");
     const int smem = TSTAGES * T_STAGE_BYTES + 1024;
-    if (kind == 1) {
-        RLA_CUDA_CHECK(cudaFuncSetAttribute(sketch_gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        sketch_gemm_tf32_kernel<1><<<(unsigned)grid, TTHREADS, smem, st>>>(mu, a);
-    } else {
-        RLA_CUDA_CHECK(cudaFuncSetAttribute(sketch_gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        sketch_gemm_tf32_kernel<2><<<(unsigned)grid, TTHREADS, smem, st>>>(mu, a);
-    }
+    static const int cl_env = getenv("RLA_GEMM32_CL") ? atoi(getenv("RLA_GEMM32_CL")) : 0;
+    const int cl = (p.mtiles % 2 == 0 && cl_env != 1) ? 2 : 1;
+    const void *fn = kind == 1 ? (cl == 2 ? (const void *)sketch_gemm_tf32_kernel<1, 2> : (const void *)sketch_gemm_tf32_kernel<1, 1>)
+                               : (cl == 2 ? (const void *)sketch_gemm_tf32_kernel<2, 2> : (const void *)sketch_gemm_tf32_kernel<2, 1>);
+    RLA_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(TTHREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    void *kargs[] = {(void *)&mu, (void *)&a};
+    RLA_CUDA_CHECK(cudaLaunchKernelExC(&cfg, fn, kargs));
     count_launch();
     RLA_CUDA_CHECK(cudaGetLastError());
     const int64_t tot = m * k_blk;
