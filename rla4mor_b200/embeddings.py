@@ -21,7 +21,12 @@ One option is new: `options['rng']`
     sketch as the reference to 1e-12;
   * 'philox' / 'philox_rademacher': Theta is generated on the fly inside the GEMM
     from a counter-based RNG and never materialised (the only way k x n = 2000 x 2**22
-    fits anywhere); `get_random_matrix()` exports exactly what the kernel used.
+    fits anywhere); `get_random_matrix()` exports exactly what the kernel used;
+  * 'philox_tf32': the normals of 'philox' rounded to TF32 (10 explicit mantissa bits).
+    With this mode (and with 'philox_rademacher') Theta is exact in TF32, and FLOAT32
+    blocks are sketched on the generation-5 tensor cores (tcgen05 kind::tf32 with a
+    two-part split of the block and FP64 accumulation of 64-term partial sums,
+    csrc/gemm32.cu: 1e-5 relative, ~4x the FP64 path); FP64 blocks use the same Theta.
 SRHT signs and row indices are always the reference's NumPy draws (bit-exact).
 """
 import logging
@@ -242,7 +247,7 @@ class RandomEmbedding:
     @property
     def _rng_mode(self):
         mode = self.options.get("rng", "mt19937")
-        assert mode in ("mt19937", "philox", "philox_rademacher"), f"unknown options['rng'] = {mode!r}"
+        assert mode in ("mt19937", "philox", "philox_rademacher", "philox_tf32"), f"unknown options['rng'] = {mode!r}"
         return mode
 
 
@@ -446,7 +451,12 @@ class GaussianEmbedding(RandomEmbedding):
             self._matrix = self._compute_matrix()
 
     def _kind(self):
-        return dense.KIND_RADEMACHER if self._rng_mode == "philox_rademacher" else dense.KIND_NORMAL
+        return {"philox_rademacher": dense.KIND_RADEMACHER, "philox_tf32": dense.KIND_NORMAL_TF32}.get(
+            self._rng_mode, dense.KIND_NORMAL)
+
+    def _tf32_ok(self):
+        """Theta exact in TF32: float32 blocks can stay float32 (tcgen05 path, csrc/gemm32.cu)."""
+        return self._rng_mode in ("philox_rademacher", "philox_tf32")
 
     def apply(self, U, mu=None):                                           # :250-254
         torch = require_cuda()
@@ -456,7 +466,7 @@ class GaussianEmbedding(RandomEmbedding):
             # slab at full GEMM height) or by groups of vectors (explicit Theta)
             from .streaming import apply_streamed, apply_streamed_rng
             assert U.shape[1] == self.source.dim
-            if self._rng_mode == "mt19937" or U.dtype != torch.float64:
+            if self._rng_mode == "mt19937" or not (U.dtype == torch.float64 or (U.dtype == torch.float32 and self._tf32_ok())):
                 return apply_streamed(self.apply, U, k, return_host=True)
             return apply_streamed_rng(self._seed, self._kind(), 1.0 / np.sqrt(k), k, U, return_host=True)
         qu, kind = self._apply_sqrt_product(U)
@@ -467,7 +477,7 @@ class GaussianEmbedding(RandomEmbedding):
             if y2 is None:
                 raise TypeError("GaussianEmbedding.apply: complex blocks need an identity sqrt_product")
             return _wrap_result(kind, self.range, torch.complex(y2[:m], y2[m:]))
-        if qu.dtype != torch.float64:
+        if qu.dtype != torch.float64 and not (qu.dtype == torch.float32 and self._tf32_ok()):
             qu = qu.to(torch.float64)
         if self._rng_mode == "mt19937":
             if self._theta_dev is None or self._theta_dev.device != qu.device:
@@ -647,12 +657,18 @@ class BlockGaussianEmbedding(RandomEmbedding):
             self._matrix = self._compute_matrix()
 
     def _kind(self):
-        return dense.KIND_RADEMACHER if self._rng_mode == "philox_rademacher" else dense.KIND_NORMAL
+        return {"philox_rademacher": dense.KIND_RADEMACHER, "philox_tf32": dense.KIND_NORMAL_TF32}.get(
+            self._rng_mode, dense.KIND_NORMAL)
+
+    def _tf32_ok(self):
+        """Theta exact in TF32: float32 blocks can stay float32 (tcgen05 path, csrc/gemm32.cu)."""
+        return self._rng_mode in ("philox_rademacher", "philox_tf32")
 
     def apply(self, U, mu=None):                                           # :425-434
         torch = require_cuda()
         V, kind = self._apply_sqrt_product(U)
-        V = V.to(torch.float64)
+        if not (V.dtype == torch.float32 and self._tf32_ok() and not V.is_complex()):
+            V = V.to(torch.float64)
         k = self.range.dim
         result = torch.empty((V.shape[0], k), dtype=torch.float64, device=V.device)
         off = 0

@@ -72,23 +72,26 @@ def apply_streamed_rng(seed, kind, scale, k, U_host, cols_per_slab=None, device=
     require_cuda()
     if isinstance(U_host, np.ndarray):
         U_host = torch.from_numpy(np.ascontiguousarray(U_host))
-    assert not U_host.is_cuda and U_host.dim() == 2 and U_host.dtype == torch.float64
+    assert not U_host.is_cuda and U_host.dim() == 2 and U_host.dtype in (torch.float64, torch.float32)
+    assert U_host.dtype == torch.float64 or kind in (dense.KIND_RADEMACHER, dense.KIND_NORMAL_TF32), \
+        "float32 host blocks need a Theta that is exact in TF32 (csrc/gemm32.cu)"
     assert U_host.stride(1) == 1
+    es = U_host.element_size()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     m, n = U_host.shape
     out = torch.zeros((m, k), dtype=torch.float64, device=device)
     if m == 0 or n == 0:
         return out
     if cols_per_slab is None:
-        cols_per_slab = max(4096, ((1 << 30) // (8 * m)) // 4096 * 4096)          # ~1 GiB per slab
-    cols_per_slab = max(16, (min(cols_per_slab, n) + 15) // 16 * 16)
+        cols_per_slab = max(4096, ((1 << 30) // (es * m)) // 4096 * 4096)         # ~1 GiB per slab
+    cols_per_slab = max(32, (min(cols_per_slab, n) + 31) // 32 * 32)
     main = torch.cuda.current_stream(device)
     copy = torch.cuda.Stream(device)
-    bufs = [torch.empty((m, cols_per_slab), dtype=torch.float64, device=device) for _ in range(2)]
+    bufs = [torch.empty((m, cols_per_slab), dtype=U_host.dtype, device=device) for _ in range(2)]
     copy.wait_stream(main)                              # see apply_streamed
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    spitch = U_host.stride(0) * 8
+    spitch = U_host.stride(0) * es
     src0 = U_host.data_ptr()
     slabs = [(c, min(c + cols_per_slab, n)) for c in range(0, n, cols_per_slab)]
     with torch.cuda.device(device):
@@ -97,7 +100,7 @@ def apply_streamed_rng(seed, kind, scale, k, U_host, cols_per_slab=None, device=
             w = c1 - c0
             if i >= 2:
                 copy.wait_event(consumed[b])
-            check(lib().rla_copy2d_async(bufs[b].data_ptr(), cols_per_slab * 8, src0 + c0 * 8, spitch, w * 8, m, 0,
+            check(lib().rla_copy2d_async(bufs[b].data_ptr(), cols_per_slab * es, src0 + c0 * es, spitch, w * es, m, 0,
                                          ctypes_stream(copy)), "rla_copy2d_async")
             copied[b].record(copy)
             main.wait_event(copied[b])

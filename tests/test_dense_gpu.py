@@ -40,7 +40,7 @@ def test_explicit_vs_oracle(dn, m, n, k):
     assert rel_fro(y.cpu().numpy(), eo.gaussian_apply(u, theta)) < TOL64
 
 
-@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("kind", [0, 1, 2])
 @pytest.mark.parametrize("m,n,k", [(5, 100, 7), (64, 4096, 64), (130, 10007, 200), (512, 30000, 130)])
 def test_rng_apply_matches_materialised_theta(dn, kind, m, n, k):
     u = np.random.RandomState(7).standard_normal((m, n))
@@ -48,6 +48,50 @@ def test_rng_apply_matches_materialised_theta(dn, kind, m, n, k):
     theta = dn.theta_materialize(1234, kind, scale, k, n).cpu().numpy()
     y = dn.embed_apply_rng(1234, kind, scale, k, _dev(u))
     assert rel_fro(y.cpu().numpy(), eo.gaussian_apply(u, theta)) < TOL64
+
+
+TOL32 = 1e-5       # north_star: relative Frobenius error of the FP32 path
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(1, 37, 3), (5, 100, 7), (64, 4096, 64), (130, 10007, 200), (256, 65536 + 24, 300),
+                                   (384, 30000, 130)])
+def test_float32_blocks_on_tcgen05(dn, kind, m, n, k):
+    """float32 blocks with a Theta exact in TF32 (csrc/gemm32.cu: tcgen05 kind::tf32, two-part split,
+    FP64 accumulation of 64-term partial sums) against the FP64 product with the SAME materialised
+    Theta; odd n, ragged m / k, single cluster (odd number of row tiles) and cluster pairs."""
+    import torch
+    u32 = np.random.RandomState(11).standard_normal((m, n)).astype(np.float32)
+    scale = 1.0 / np.sqrt(k)
+    theta = dn.theta_materialize(99, kind, scale, k, n).cpu().numpy()
+    y = dn.embed_apply_rng(99, kind, scale, k, torch.from_numpy(u32).cuda())
+    assert y.dtype == torch.float64
+    ref = eo.gaussian_apply(u32.astype(np.float64), theta)
+    assert rel_fro(y.cpu().numpy(), ref) < TOL32
+    # the FP64 kernel on the widened block uses the same Theta
+    y64 = dn.embed_apply_rng(99, kind, scale, k, torch.from_numpy(u32.astype(np.float64)).cuda())
+    assert rel_fro(y64.cpu().numpy(), ref) < TOL64
+
+
+def test_tf32_theta_is_exact_in_tf32(dn):
+    t = dn.theta_materialize(3, 2, 1.0, 64, 4096).cpu().numpy().astype(np.float32)
+    bits = t.view(np.uint32)
+    assert np.all(bits & np.uint32(0x1FFF) == 0)                   # 13 low mantissa bits are zero
+    t0 = dn.theta_materialize(3, 0, 1.0, 64, 4096).cpu().numpy()
+    assert np.max(np.abs(t - t0) / np.maximum(np.abs(t0), 1e-30)) <= 2.0 ** -11 * 1.0001
+    assert abs(t.std() - 1.0) < 5e-3
+
+
+def test_float32_column_offsets_accumulate(dn):
+    """Column slabs of a float32 block accumulate to the whole sketch (what streaming.py does)."""
+    import torch
+    m, n, k = 130, 3 * 4096, 96
+    u = torch.from_numpy(np.random.RandomState(2).standard_normal((m, n)).astype(np.float32)).cuda()
+    whole = dn.embed_apply_rng(7, 2, 0.5, k, u)
+    acc = torch.zeros((m, k), dtype=torch.float64, device="cuda")
+    for i, c0 in enumerate(range(0, n, 4096)):
+        dn.embed_apply_rng(7, 2, 0.5, k, u[:, c0:c0 + 4096].contiguous(), col0=c0, out=acc, accumulate=i > 0)
+    assert rel_fro(acc.cpu().numpy(), whole.cpu().numpy()) < 1e-6
 
 
 def test_rng_statistics_and_determinism(dn):

@@ -113,6 +113,30 @@ def test_gaussian_embedding_on_the_fly(rb):
         rb.GaussianEmbedding(source=rb.DeviceVectorSpace(8), options={"range_dim": 2, "rng": "bogus"}).apply(np.zeros((1, 8)))
 
 
+def test_float32_blocks_through_the_embedding_classes(rb):
+    """options['rng'] = 'philox_tf32' / 'philox_rademacher': float32 blocks (device, NumPy, pinned host)
+    go through the tcgen05 path and match `U @ get_random_matrix().T` to the FP32 tolerance; FP64
+    blocks use the same Theta to 1e-12."""
+    import torch
+    n, k = 20000, 150
+    x32 = np.random.RandomState(4).standard_normal((70, n)).astype(np.float32)
+    for mode in ("philox_tf32", "philox_rademacher"):
+        emb = rb.GaussianEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k, "rng": mode}, _seed=5)
+        theta = emb.get_random_matrix()
+        ref = eo.gaussian_apply(x32.astype(np.float64), theta)
+        assert rel_fro(emb.apply(x32), ref) < 1e-5                                    # NumPy float32 block
+        assert rel_fro(emb.apply(torch.from_numpy(x32).cuda()).cpu().numpy(), ref) < 1e-5
+        host = torch.from_numpy(x32).pin_memory()
+        assert rel_fro(emb.apply(host).numpy(), ref) < 1e-5                           # streamed by column slabs
+        assert rel_fro(emb.apply(x32.astype(np.float64)), ref) < TOL                  # same Theta for FP64 blocks
+    b = rb.BlockGaussianEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k, "max_block_size": 64, "rng": "philox_tf32"}, _seed=9)
+    refb = eo.gaussian_apply(x32.astype(np.float64), b.get_random_matrix())
+    assert rel_fro(b.apply(x32), refb) < 1e-5
+    # 'philox' (unrounded normals) keeps float32 blocks on the FP64 path
+    e0 = rb.GaussianEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k, "rng": "philox"}, _seed=5)
+    assert rel_fro(e0.apply(x32), eo.gaussian_apply(x32.astype(np.float64), e0.get_random_matrix())) < TOL
+
+
 def test_block_gaussian_embedding(rb):
     z = emb_golden()
     for tag in ("block_a", "block_b"):
