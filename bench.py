@@ -9,6 +9,9 @@ A step is one pass of the hot path over one block of synthetic vectors.  Workloa
 (BASELINE.json `configs`):
     gauss_c2 (default)  Gaussian embedding k=2000 on a float64 2^22 x 512 block, Theta
                         generated on the fly (configs[1]; FP64 tensor-pipe bound)
+    gauss_c2_f32        the same shape with a FLOAT32 block on the generation-5 tensor cores
+                        (tcgen05 kind::tf32, Theta = normals rounded to TF32, FP64 accumulation of
+                        64-term partial sums; 1e-5 tolerance); `secondary`
     srht_c3             SRHT k=4000 on a float64 2^24 x 1024 block, column-sharded
                         (configs[2]; HBM bound); run as the `secondary` result
     srht_c1             SRHT k=1000 on 2^16 x 200 (configs[0], the one case the reference runs in
@@ -41,6 +44,8 @@ WORKLOADS = {
     "gauss_c2": dict(kind="gauss", m=512, logn=22, k=2000, config="configs[1]"),
     "srht_c3": dict(kind="srht", m=1024, logn=24, k=4000, config="configs[2]"),
     "srht_c1": dict(kind="srht", m=200, logn=16, k=1000, config="configs[0]"),
+    # configs[1] with a float32 block: the optional FP32 path of north_star (tcgen05 kind::tf32)
+    "gauss_c2_f32": dict(kind="gauss32", m=512, logn=22, k=2000, config="configs[1] (float32 block, optional FP32 path)"),
 }
 
 
@@ -52,10 +57,11 @@ def workload_config(name, world, m_loc=None, note=None):
     if m_loc is None:
         m_loc = wl["m"] // world if strong else wl["m"]
     m_total = m_loc * world
+    esz = 4 if wl["kind"] == "gauss32" else 8
     cfg = {"workload": name, "baseline_config": wl["config"], "embedding": wl["kind"], "m_total": m_total,
            "m_per_gpu": m_loc, "n": n, "k": wl["k"], "partition": f"columns x{world} (no collective)",
            "scaling": "strong" if strong else "weak",
-           "l2": ("inputs larger than L2 (per-GPU block %.1f GB >> 126 MB)" % (m_loc * n * 8 / 1e9)) if m_loc * n * 8 > 2e8
+           "l2": ("inputs larger than L2 (per-GPU block %.1f GB >> 126 MB)" % (m_loc * n * esz / 1e9)) if m_loc * n * esz > 2e8
            else "L2 flushed between timed steps (256 MB write); per-step CUDA events"}
     if note:
         cfg["note"] = note
@@ -197,7 +203,7 @@ def run_reference(args):
     wl = WORKLOADS[args.workload]
     m, n, k = wl["m"], 2 ** wl["logn"], wl["k"]
     extrapolated = True
-    if wl["kind"] == "gauss":
+    if wl["kind"] in ("gauss", "gauss32"):                # the CPU reference has one Gaussian path (float64 Theta)
         kb = 50
         U = host_block(m, n)
         step = lambda: cpu_gauss_sample(U, k, kb)
@@ -339,7 +345,9 @@ def run_ours(args):
             m_loc = fit
             m_total = m_loc * world
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-        U = torch.empty((m_loc, n), dtype=torch.float64, device=dev)
+        dt_in = torch.float32 if wl["kind"] == "gauss32" else torch.float64
+        esz = 4 if wl["kind"] == "gauss32" else 8
+        U = torch.empty((m_loc, n), dtype=dt_in, device=dev)
         for lo in range(0, m_loc, 32):                      # in-place fill, no 2x temporary
             U[lo:lo + 32].normal_(generator=gen)
         out = torch.empty((m_loc, k), dtype=torch.float64, device=dev)
@@ -365,6 +373,18 @@ def run_ours(args):
                                     "MEASURED_PEAKS.json has no FP64 entry",
                         cublas_dgemm_tflops_same_run=cublas_tf,
                         algorithmic="2*k*n*m flops per launch, Theta generated in-kernel (no bytes)")
+        elif wl["kind"] == "gauss32":
+            emb = rb.GaussianEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k, "rng": "philox_tf32"}, _seed=0)
+            step = lambda: dense.embed_apply_rng(0, dense.KIND_NORMAL_TF32, 1.0 / np.sqrt(k), k, U, out=out)
+            apply_fn = emb.apply
+            work = 2.0 * k * n * m_loc
+            tf32_peak = float(peaks.get("bf16_tflops", 1618.2)) / 2.0
+            roof = dict(bound="tensor", unit="TFLOP/s", peak=tf32_peak,
+                        peak_source="half of the measured dense bf16 figure (MEASURED_PEAKS.json): kind::tf32 runs at half the bf16 rate",
+                        algorithmic="2*k*n*m flops per launch (Theta generated in-kernel, no bytes); the kernel issues TWO "
+                                    "tf32 MMAs per product (two-part split of the block), so the tensor pipe is busy at twice "
+                                    "`frac`; the bound of this kernel is the Theta generator (1024 Philox blocks per 128 x 128 x 32 "
+                                    "stage), not the tensor pipe")
         else:
             emb = rb.SrhtEmbedding(source=rb.DeviceVectorSpace(n), options={"range_dim": k}, _seed=0)
             plan = emb._plan(torch.float64, dev)
@@ -373,7 +393,7 @@ def run_ours(args):
             work = float(m_loc * n * 8 + m_loc * k * 8 + n + 4 * k)   # algorithmic bytes per rank per step
             roof = dict(bound="hbm", unit="GB/s", peak=float(peaks["hbm_gbs"]), peak_source=peak_src,
                         algorithmic="m*n*8 (read U once) + m*k*8 (write sketch) + n (signs) + 4k (indices) bytes per launch")
-        small = m_loc * n * 8 < 2e8                          # fits L2: flush between steps
+        small = m_loc * n * esz < 2e8                        # fits L2: flush between steps
         ms, launches, clocks = timed(step, steps, warmup, flush=small)
         t_step = ms / steps / 1e3
         achieved = work / t_step / (1e12 if roof["bound"] == "tensor" else 1e9)
@@ -389,10 +409,11 @@ def run_ours(args):
                     achieved_best_step=work / best / (1e12 if roof["bound"] == "tensor" else 1e9),
                     step_ms=[round(v, 3) for v in timed.last_step_ms],
                     kernel="sketch_gemm_kernel" if wl["kind"] == "gauss" else
+                    "sketch_gemm_tf32_kernel" if wl["kind"] == "gauss32" else
                     ("srht_ws_kernel" if m_loc * (n // 4096) >= 16384 else "srht_main_kernel"),
                     note="duration = whole step (main kernel + its small reduce/finalize kernel), CUDA events")
         res = {
-            "workload": name, "value": m_total * n * 8 / t_step / 1e9, "unit": "GB/s",
+            "workload": name, "value": m_total * n * esz / t_step / 1e9, "unit": "GB/s",
             "cols_per_s": m_total / t_step, "ms_per_step": ms / steps, "gpu_launches": launches,
             "roofline": roof, "clocks": clocks,
             "config": workload_config(name, world, m_loc, note),
@@ -403,17 +424,17 @@ def run_ours(args):
                                   "profiles/srht_r02_experiments.txt); the 13 FP64 adds per element then run at that clock")
         # ---- end to end: host (pinned) block -> H2D -> sketch -> D2H of the result, per step
         if with_e2e:
-            m_e = min(m_loc, max(1, (20 << 30) // (n * 8)))           # at most ~20 GiB of pinned memory
+            m_e = min(m_loc, max(1, (20 << 30) // (n * esz)))         # at most ~20 GiB of pinned memory
             try:
-                host = torch.empty((m_e, n), dtype=torch.float64, pin_memory=True)
+                host = torch.empty((m_e, n), dtype=dt_in, pin_memory=True)
                 host.copy_(U[:m_e])
                 torch.cuda.synchronize()
                 e_step = lambda: apply_fn(host)                       # host block in, host sketch out
                 e_steps = max(2, min(steps, 5))
                 ems, _, _ = timed(e_step, e_steps, 1, flush=small)
                 te = ems / e_steps / 1e3
-                res["e2e"] = {"value": m_e * world * n * 8 / te / 1e9, "unit": "GB/s",
-                              "h2d_bytes_per_step": int(m_e * n * 8), "d2h_bytes_per_step": int(m_e * k * 8),
+                res["e2e"] = {"value": m_e * world * n * esz / te / 1e9, "unit": "GB/s",
+                              "h2d_bytes_per_step": int(m_e * n * esz), "d2h_bytes_per_step": int(m_e * k * 8),
                               "api": f"{type(emb).__name__}.apply(pinned host block) -> pinned host sketch; ~1 GiB pieces "
                                      "copied on a side stream under the sketch of the previous piece (streaming.py)",
                               "m_per_gpu": m_e, "ms_per_step": ems / e_steps, "cols_per_s": m_e * world / te}
@@ -453,6 +474,14 @@ def run_ours(args):
         secondary[-1].pop("_host_block", None)
     primary = run_workload(args.workload, not args.no_e2e, not args.no_cpu_baseline, args.steps, args.warmup)
     host_block_np = primary.pop("_host_block", None)
+    if not args.no_secondary and args.workload == "gauss_c2":
+        try:
+            secondary.append(run_workload("gauss_c2_f32", not args.no_e2e, False, max(3, min(args.steps, 10)), max(3, args.warmup)))
+            secondary[-1].pop("_host_block", None)
+            if secondary[-1].get("roofline"):
+                secondary[-1]["dtype"] = "f32 block, tf32 x 2 tensor-core products, FP64 accumulation of 64-term partial sums"
+        except Exception as exc:
+            secondary.append({"workload": "gauss_c2_f32", "error": f"{type(exc).__name__}: {exc}"[:300]})
 
     if not args.no_secondary and args.workload == "gauss_c2":
         # configs[4]: row-sharded range finder (sketch + NVLink peer-memory exchange + thin QR / SVD)
