@@ -27,7 +27,8 @@
 // warps at 40 = 60 416, and per sub-partition (warp w lives on w % 4) 2 x 176 + 3 x 40 warps.
 // (A first version asked for more than its pool held: the flush warps waited for ever.)
 // The kernel is bound by the generator (1024 Philox blocks per stage against 512 cycles of MMA):
-// hence ten producer warps.
+// hence ten producer warps.  Measured dead end: letting the (mostly idle) flush warps do the split
+// of the U tile, with four TMEM buffers so that no flush is ever waited for: 146 vs 157 TFLOP/s.
 // Two accumulator buffers in TMEM (2 x 128 columns): MMAs of chunk c + 1 run while chunk c is flushed.
 #include "common.cuh"
 #include "rng.cuh"

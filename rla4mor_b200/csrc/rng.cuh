@@ -61,10 +61,11 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, fl
     n1 = r * s;
 }
 
+// round to nearest TF32, ties away from zero -- what cvt.rna.tf32.f32 does for finite values -- as
+// two integer instructions (half an ulp of the 10-bit mantissa added to the magnitude, 13 bits
+// cleared): the conversion would run on the XU pipe, which the generator already loads with MUFU
 __device__ __forceinline__ float round_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // the four entries Theta[row, 4*q .. 4*q+3]  (q = col / 4) as floats, unscaled
