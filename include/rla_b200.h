@@ -248,6 +248,21 @@ int rla_svd_jacobi_block_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
                              double *s_dev, double *V_dev, const int32_t *sched_dev, int B,
                              int32_t *scratch_dev, int max_sweeps, double tol, void *stream);
 
+/* Cluster-resident one-sided Jacobi SVD (csrc/jacobi_cluster.cu; same data convention as
+ * rla_svd_jacobi_f64): the whole (m, k [+ m]) row block lives in the distributed shared memory of
+ * ONE thread-block cluster of C CTAs for the whole iteration; block rounds of the circle-method
+ * tournament end with a DSMEM push and a cluster barrier instead of a trip through global memory.
+ * rla_svd_jacobi_cluster_size returns C (2, 4, 8 or 16) or 0 when the shape does not fit (then
+ * use rla_svd_jacobi_block_f64 / rla_svd_jacobi_f64).  info_dev: 8 int32, on return {sweeps
+ * done, converged, 0, then five phase counters in kilo-cycles of CTA 0: stage load + norms,
+ * rotation steps, wait on the stage barrier, push, end-of-round barrier}.  One launch, no host synchronisation, no flags in global memory (the
+ * hardware co-schedules the CTAs of a cluster, so there is no timeout path).  This is the SVD
+ * of the "thin QR / SVD of the k x m sketch" of BASELINE configs[4]. */
+int rla_svd_jacobi_cluster_size(int64_t k, int64_t m, int want_v);
+int rla_svd_jacobi_cluster_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
+                               double *s_dev, double *V_dev, int32_t *info_dev,
+                               int max_sweeps, double tol, void *stream);
+
 /* T = R^-1 for the upper-triangular r x r factor of Gram-Schmidt (row-major): the reference's
  * T = pinv(R) (mor/sketched_reductor.py:95) when no row was removed. */
 int rla_trinv_upper_f64(const double *R_dev, int64_t r, int64_t ldr, double *T_dev, int64_t ldt, void *stream);

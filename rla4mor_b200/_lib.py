@@ -64,6 +64,8 @@ _SIGS = {
     "rla_svd_jacobi_block_rows": (c_int, [c_int64, c_int64, c_int]),
     "rla_svd_jacobi_block_scratch_ints": (c_size_t, [c_int64, c_int, c_int]),
     "rla_svd_jacobi_block_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, c_int, c_double, _vp]),
+    "rla_svd_jacobi_cluster_size": (c_int, [c_int64, c_int64, c_int]),
+    "rla_svd_jacobi_cluster_f64": (c_int, [_vp, c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, c_double, _vp]),
     "rla_trinv_upper_f64": (c_int, [_vp, c_int64, c_int64, _vp, c_int64, _vp]),
     "rla_sptrsv_plan_host": (c_int, [c_int64, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _vp, _vp, _vp, POINTER(c_int64), _vp, _vp, _vp, _vp, POINTER(c_int64),

@@ -129,11 +129,15 @@ def _round_robin(m, keep_bye=False):
 _PAIRS = {}
 
 
-def svd_jacobi(S, want_v=False, max_sweeps=30, tol=None, block=True):
+def svd_jacobi(S, want_v=False, max_sweeps=30, tol=None, block=True, cluster=True):
     """One-sided Jacobi SVD of the k x m sketch held as a row block S (m, k).
     Returns (U_rows (m, k) orthonormal rows, s (m,), V (m, m) or None), singular values
     sorted descending: S = (V^T diag(s) U_rows) in the row layout, i.e. the k x m matrix
-    S^T = U_rows^T diag(s) V."""
+    S^T = U_rows^T diag(s) V.
+
+    Three kernels, in order of preference: the cluster-resident one (`cluster`; the whole
+    block in the distributed shared memory of one thread-block cluster, csrc/jacobi_cluster.cu),
+    the grid-synchronised block kernel (`block`; csrc/factor.cu) and the launch-per-round one."""
     A = _rows(S).to(torch.float64).clone()
     m, k = A.shape
     if tol is None:
@@ -142,9 +146,18 @@ def svd_jacobi(S, want_v=False, max_sweeps=30, tol=None, block=True):
         tol = max(1.0, np.sqrt(k)) * 1.1102230246251565e-16
     s = torch.empty((m,), dtype=torch.float64, device=A.device)
     V = torch.empty((m, m), dtype=torch.float64, device=A.device) if want_v else None
-    B = lib().rla_svd_jacobi_block_rows(k, m, 1 if want_v else 0) if (block and A.data_ptr() % 16 == 0
-                                                                       and A.stride(0) % 2 == 0) else 0
-    if B:
+    aligned = A.data_ptr() % 16 == 0 and A.stride(0) % 2 == 0
+    C = lib().rla_svd_jacobi_cluster_size(k, m, 1 if want_v else 0) if (cluster and aligned) else 0
+    B = lib().rla_svd_jacobi_block_rows(k, m, 1 if want_v else 0) if (block and aligned and not C) else 0
+    if C:
+        # one launch of ONE cluster: block pairs in distributed shared memory (csrc/jacobi_cluster.cu)
+        scratch = torch.zeros((8,), dtype=torch.int32, device=A.device)
+        with torch.cuda.device(A.device):
+            check(lib().rla_svd_jacobi_cluster_f64(A.data_ptr(), k, m, A.stride(0), s.data_ptr(),
+                                                   V.data_ptr() if want_v else None, scratch.data_ptr(),
+                                                   int(max_sweeps), float(tol), stream_ptr()),
+                  "rla_svd_jacobi_cluster_f64")
+    elif B:
         # one persistent launch: block pairs in shared memory, grid barrier per block round (csrc/factor.cu)
         nblk = -(-m // B)
         key = ("blk", nblk, A.device.index)
@@ -169,7 +182,8 @@ def svd_jacobi(S, want_v=False, max_sweeps=30, tol=None, block=True):
                                            int(max_sweeps), float(tol), ctypes.byref(done), stream_ptr()),
                   "rla_svd_jacobi_f64")
     order = torch.argsort(s, descending=True)
-    if B:
+    if B or C:
+        svd_jacobi.last_phases = scratch[3:8].tolist() if C else None   # kilo-cycles per phase (cluster kernel)
         info = scratch[:3].cpu()                    # {sweeps, converged, timeout}; the sort above follows the launch anyway
         if int(info[2]) != 0:
             raise RlaError("svd_jacobi: the block kernel timed out waiting on a block flag; result discarded")

@@ -71,6 +71,9 @@ def test_new_entry_points_validate_arguments_without_gpu():
     assert lib.rla_sptrsv_group_inverses_host(2, None, None, None, None, None, 0, None, None, None, None, None) == -1
     assert lib.rla_svd_jacobi_block_scratch_ints(256, 8, 30) == 30 + 32 + 8
     assert lib.rla_svd_jacobi_block_rows(1024, 256, 1) in (0, 2, 4, 8)          # 0 without a device
+    assert lib.rla_svd_jacobi_cluster_size(256, 256, 0) in (0, 16)              # 0 without a device
+    assert lib.rla_svd_jacobi_cluster_size(255, 256, 0) == 0                    # odd row length: not supported
+    assert lib.rla_svd_jacobi_cluster_size(1024, 256, 1) == 0                   # 256 x 1280 does not fit 16 CTAs
     # odd ldx / negative sizes / null pointers -> RLA_ERR_INVALID (-1), no device touched
     assert lib.rla_sptrsv_transpose_in_f64(None, 3, 10, 10, None, None, 3, None) == -1
     assert lib.rla_sptrsv_permute_rows_f64(None, None, None, 5, 3, None) == -1

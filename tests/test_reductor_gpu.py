@@ -115,16 +115,45 @@ def test_gram_schmidt_grid_kernel_semantics(rb):
     assert rel_fro((R1.T @ Q1).cpu().numpy(), B) < 1e-13                  # A = R^T Q
 
 
+@pytest.mark.parametrize("m,k,want_v,force", [(64, 128, False, 2), (64, 128, True, 4), (64, 128, False, 8),
+                                              (64, 128, True, 16), (256, 256, False, 0), (256, 256, True, 0),
+                                              (256, 1024, False, 0), (100, 130, True, 0), (500, 512, False, 0)])
+def test_jacobi_cluster_kernel(rb, m, k, want_v, force, monkeypatch):
+    """Cluster-resident Jacobi (csrc/jacobi_cluster.cu): every cluster size, with and without the
+    accumulated rotations, ragged m, against numpy and against the grid-synchronised block kernel."""
+    from rla4mor_b200 import reductor_ops as ops
+    if force:
+        monkeypatch.setenv("RLA_JACOBI_CLUSTER", str(force))
+    C = rb.lib().rla_svd_jacobi_cluster_size(k, m, 1 if want_v else 0)
+    assert C == (force or C) and C in (2, 4, 8, 16), C                   # the cluster kernel applies
+    S = np.random.RandomState(m + k).standard_normal((m, k)) * np.logspace(0, -5, m)[:, None]
+    U, s, V = ops.svd_jacobi(_dev(S), want_v=want_v)
+    info = [int(v) for v in ops.svd_jacobi.last_info.tolist()]
+    assert info[1] == 1 and info[0] < 20, info
+    s_ref = np.linalg.svd(S, compute_uv=False)
+    assert np.max(np.abs(s.cpu().numpy() - s_ref) / s_ref[0]) < 1e-13
+    assert np.max(np.abs(s.cpu().numpy() - s_ref) / s_ref) < 1e-9        # high relative accuracy
+    r_num = min(m, k)
+    Un = U[:r_num].cpu().numpy()
+    assert rel_fro(Un @ Un.T, np.eye(r_num)) < 1e-10
+    if want_v:
+        assert rel_fro(((V.T * s) @ U).cpu().numpy(), S) < 1e-12
+        assert rel_fro((V @ V.T).cpu().numpy(), np.eye(m)) < 1e-12
+    monkeypatch.setenv("RLA_JACOBI_CLUSTER", "0")
+    U2, s2, V2 = ops.svd_jacobi(_dev(S), want_v=want_v)
+    assert np.max(np.abs((s - s2).cpu().numpy()) / s_ref[0]) < 1e-13
+
+
 def test_jacobi_block_vs_round_kernel(rb):
     from rla4mor_b200 import reductor_ops as ops
     S = np.random.RandomState(11).standard_normal((70, 512)) * np.logspace(0, -9, 70)[:, None]
-    U1, s1, V1 = ops.svd_jacobi(_dev(S), want_v=True)
-    U2, s2, V2 = ops.svd_jacobi(_dev(S), want_v=True, block=False)
+    U1, s1, V1 = ops.svd_jacobi(_dev(S), want_v=True, cluster=False)
+    U2, s2, V2 = ops.svd_jacobi(_dev(S), want_v=True, block=False, cluster=False)
     s_ref = np.linalg.svd(S, compute_uv=False)
     assert np.max(np.abs(s1.cpu().numpy() - s_ref) / s_ref) < 1e-9        # high RELATIVE accuracy (Jacobi)
     assert np.max(np.abs(s2.cpu().numpy() - s_ref) / s_ref) < 1e-9
     assert rel_fro(((V1.T * s1) @ U1).cpu().numpy(), S) < 1e-12
-    U3, s3, _ = ops.svd_jacobi(_dev(S), want_v=False)
+    U3, s3, _ = ops.svd_jacobi(_dev(S), want_v=False, cluster=False)
     assert np.max(np.abs(s3.cpu().numpy() - s_ref) / s_ref) < 1e-9
 
 

@@ -116,11 +116,25 @@ def run_c5(rank, world, dev, steps=10, warmup=3, hbm_peak=None, dmma_peak=None):
     info_direct = [int(v) for v in ops.svd_jacobi.last_info.tolist()] if hasattr(ops.svd_jacobi, "last_info") else None
     rangefinder.sketch_svd(S)
     info_pre = [int(v) for v in ops.svd_jacobi.last_info.tolist()] if hasattr(ops.svd_jacobi, "last_info") else None
-    t_svd_old, _ = timed(lambda: ops.svd_jacobi(S, want_v=True, block=False), 2, 1)
+    phases_pre = getattr(ops.svd_jacobi, "last_phases", None)
+    t_svd_old, _ = timed(lambda: ops.svd_jacobi(S, want_v=True, block=False, cluster=False), 2, 1)
+    t_svd_grid, _ = timed(lambda: ops.svd_jacobi(S, want_v=True, cluster=False), 2, 1)
+    # the Jacobi iteration alone on the m x m triangular factor (what sketch_svd runs after the QR)
+    Rf = rangefinder.thin_qr(S)[1]
+    Rp = torch.zeros((Rf.shape[0], M + (M & 1)), dtype=torch.float64, device=dev)
+    Rp[:, :M] = Rf
+    t_jac_cluster, _ = timed(lambda: ops.svd_jacobi(Rp, want_v=False), max(2, steps // 2), 1)
+    t_jac_grid, _ = timed(lambda: ops.svd_jacobi(Rp, want_v=False, cluster=False), 2, 1)
     out["factorisation"] = {"thin_qr_ms": t_qr, "svd_ms": t_svd, "gram_schmidt_pymor_semantics_ms": t_gs,
-                            "svd_block_jacobi_direct_ms": t_svd_direct, "svd_round_per_launch_ms": t_svd_old,
-                            "block_jacobi_info_direct(sweeps,converged,timeout)": info_direct,
-                            "block_jacobi_info_preconditioned": info_pre}
+                            "jacobi_on_R_cluster_kernel_ms": t_jac_cluster,
+                            "jacobi_on_R_grid_synchronised_kernel_ms": t_jac_grid,
+                            "cluster_kernel": {"cluster_size": int(lib.rla_svd_jacobi_cluster_size(Rp.shape[1], Rp.shape[0], 0)),
+                                               "phase_kilocycles(stage load, rotation steps, stage barrier, push, "
+                                               "round barrier)": phases_pre},
+                            "svd_direct_on_sketch_ms": t_svd_direct, "svd_direct_grid_synchronised_ms": t_svd_grid,
+                            "svd_round_per_launch_ms": t_svd_old,
+                            "jacobi_info_direct(sweeps,converged,timeout)": info_direct,
+                            "jacobi_info_preconditioned": info_pre}
     # whole range finder step, SRHT when the world size allows it
     kind = "srht" if "srht" in out else "gauss"
     t_all, l_all = timed(lambda: rangefinder.sketched_range_finder(U, n, K, 0, kind, rank, world, reducer=reducer),
