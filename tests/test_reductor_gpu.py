@@ -196,10 +196,11 @@ def test_sketch_svd_w_from_triangular_inverse(rb):
 
 def test_pinv_R_triangular_inverse(rb):
     from rla4mor_b200 import reductor_ops as ops
-    for r in (1, 5, 64, 257):
-        R = np.triu(np.random.RandomState(r).standard_normal((r, r))) + 3.0 * np.eye(r)
+    for r in (1, 5, 31, 32, 33, 64, 128, 129, 256, 257, 600, 1024, 1100):      # row kernel up to 1024, column kernel beyond
+        R = np.triu(np.random.RandomState(r).standard_normal((r, r))) / np.sqrt(r) + 3.0 * np.eye(r)
         T = ops.pinv_R(_dev(R)).cpu().numpy()
         assert rel_fro(T, np.linalg.inv(R)) < 1e-12 and np.all(np.tril(T, -1) == 0.0)
+        assert rel_fro(T @ R, np.eye(r)) < 1e-13
     Rr = np.random.RandomState(0).standard_normal((3, 5))
     assert rel_fro(ops.pinv_R(_dev(Rr)).cpu().numpy(), np.linalg.pinv(Rr)) < 1e-12
 
