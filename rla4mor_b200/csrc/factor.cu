@@ -98,20 +98,97 @@ __device__ __forceinline__ void block_sum_n(double (&v)[N], double (*red)[32]) {
     }
 }
 
+template <int N> struct Log2 { static constexpr int v = 1 + Log2<N / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+// Warp sums of N values per lane at once (N a power of two <= 16): at every level half of the
+// values go to the partner lane, so the count halves while the sums grow -- the same additions as N
+// butterflies (same pairs at every level, bit-identical sums) with N - 1 + (5 - log2 N) shuffles
+// instead of 5 N.  On return v[0] of lane l is the warp sum of the ORIGINAL v[l >> (5 - log2 N)].
+template <int N>
+__device__ __forceinline__ void warp_reduce_multi(double (&v)[N], int lane) {
+    constexpr int LG = Log2<N>::v;
+#pragma unroll
+    for (int s = 0; s < LG; ++s) {
+        const int M = N >> s, o = 16 >> s;
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < M / 2; ++j) {
+            const double send = upper ? v[j] : v[j + M / 2];
+            const double keep = upper ? v[j + M / 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+#pragma unroll
+    for (int o = 16 >> LG; o; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+
+// block_sum_n for the 256-thread Gram-Schmidt CTAs: multi-value warp reduction, the eight warp
+// partials read back with 16-byte loads and added in warp order (no loop, no dependent loads).
+// red: [N][8] doubles, 16-byte aligned.  Same sums, bit for bit, as block_sum_n.
+template <int N>
+__device__ __forceinline__ void block_sum8(double (&v)[N], double (*red)[8]) {
+    constexpr int SH = 5 - Log2<N>::v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    warp_reduce_multi<N>(v, lane);
+    __syncthreads();                                   // previous readers of `red` are done
+    if ((lane & ((1 << SH) - 1)) == 0) red[lane >> SH][warp] = v[0];
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const double2 a = *reinterpret_cast<const double2 *>(&red[n][0]), b = *reinterpret_cast<const double2 *>(&red[n][2]);
+        const double2 c = *reinterpret_cast<const double2 *>(&red[n][4]), d = *reinterpret_cast<const double2 *>(&red[n][6]);
+        v[n] = ((((((0.0 + a.x) + a.y) + b.x) + b.y) + c.x) + c.y) + d.x + d.y;
+    }
+}
+
 constexpr int GS_MAX_REITER = 3;
 enum { GS_REMOVED = 1, GS_FINAL = 2, GS_REITER = 3 };
 
-// Workspace: scratch G*k doubles | coef r doubles | ctrl (GS_MAX_REITER+1)*r int32 | done (same) | status int32.
-// ctrl[e]: decision of event e (0 = not yet published); done[e]: CTAs that contributed to re-iteration e.
+// Publication of a finished row WITHOUT a fence or a flag (round 2; the "LL" protocol collective
+// libraries use for small messages): every double travels as two 8-byte words {32 data bits, 32-bit
+// sequence tag}, written with one 16-byte store per element into the ring slot of the event; the
+// tag = (event + 1) * 4 + decision.  A reader polls the very words it needs (its own EPT elements)
+// until both halves of each carry the tag of the event it waits for: data and "ready" arrive in
+// the same 8-byte atomic word, so there is no flag to order against and no memory fence on the
+// writer's critical path (the release store after the 8 KB row write was ~60 % of the 3.8 us the
+// owner of a row spent between receiving q_{i-1} and handing over q_i).  Slots are zeroed by the
+// host before the launch (tag 0 never matches) and a slot is re-used after GS_LL_SLOTS(G) events:
+// a CTA publishes only after it has consumed every earlier event and owns one row in any G
+// consecutive rows, so nobody lags more than (GS_MAX_REITER + 1) (G + 1) events.
+__device__ __forceinline__ void ll_store_f64(unsigned long long *p, double v, uint32_t tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = (b & 0xffffffffull) | t, w1 = (b >> 32) | t;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+// Reading side, in three branch-free pieces so that a thread can have ALL its loads in flight
+// before it looks at any of them (a validity branch between two loads serialises them: one L2
+// round trip per word instead of one per batch).
+__device__ __forceinline__ void ll_ld(const unsigned long long *p, unsigned long long &w0, unsigned long long &w1) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+// both words carry a tag of event `want` (= event + 1)
+__device__ __forceinline__ bool ll_valid(unsigned long long w0, unsigned long long w1, uint32_t want) {
+    const uint32_t t0 = (uint32_t)(w0 >> 32), t1 = (uint32_t)(w1 >> 32);
+    return ((t0 >> 2) == want) & (t1 == t0);
+}
+__device__ __forceinline__ double ll_value(unsigned long long w0, unsigned long long w1) {
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+__device__ __forceinline__ int ll_decision(unsigned long long w0) { return (int)((w0 >> 32) & 3ull); }
+
+// Workspace: status int32 | ll: GS_LL_SLOTS(G) ring slots of 2 * EPT * 256 words (row hand-over), then G
+// partial slots (+ 2 RPC coefficient words each) and G leader slots (re-iteration, see below).
 template <int RPC, int EPT>
 __global__ void __launch_bounds__(256, 1)
 gs_grid_kernel(double *A, int64_t r, int64_t k, int64_t lda, int64_t offset, double *R,
-               int32_t *flags, double atol, double rtol, double thr, double *scratch, double *coef,
-               int32_t *ctrl, int32_t *done, int32_t *status, unsigned long long timeout_ns) {
+               int32_t *flags, double atol, double rtol, double thr,
+               unsigned long long *ll, int nslot, int32_t *status, unsigned long long timeout_ns, int poll_mode) {
     // (no __restrict__: other CTAs write these buffers while the kernel runs)
-    __shared__ double red[RPC][32];
-    __shared__ int s_slot;
+    __shared__ __align__(16) double red[RPC][8];
     const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    constexpr int64_t SLOT_WORDS = 2 * (int64_t)EPT * 256;
+    constexpr int64_t PART_WORDS = SLOT_WORDS + 2 * RPC;   // a partial correction + the RPC coefficients behind it
     double x[RPC][EPT];
     double init[RPC], nrm[RPC];
     int state[RPC];                                    // 0 pending, 1 final (orthonormal), 2 removed / absent
@@ -128,11 +205,11 @@ gs_grid_kernel(double *A, int64_t r, int64_t k, int64_t lda, int64_t offset, dou
                 x[s][e] = (l < r && c < k) ? A[l * lda + c] : 0.0;
                 ss[s] = fma(x[s][e], x[s][e], ss[s]);
             }
-            // column l of R belongs to this CTA alone: identity, then += as projections arrive
+            // column l of R belongs to this CTA alone: identity, then the projections as they arrive
             if (l < r)
                 for (int64_t j = tid; j < r; j += nthr) R[j * r + l] = (j == l) ? 1.0 : 0.0;
         }
-        block_sum_n<RPC>(ss, red);
+        block_sum8<RPC>(ss, red);
 #pragma unroll
         for (int s = 0; s < RPC; ++s) {
             const int64_t l = (int64_t)s * G + cta;
@@ -143,91 +220,147 @@ gs_grid_kernel(double *A, int64_t r, int64_t k, int64_t lda, int64_t offset, dou
         __syncthreads();
     }
 
-    // owner side of one decision event for row i (slot sl of this CTA); publishes ctrl[e]
-    auto decide = [&](int64_t i, int sl, int iter, int64_t e) {
+    // Owner side of one decision event for row i (slot sl of this CTA): optionally projects q_prev
+    // out of the row first (the look-ahead), judges it, publishes the row (and the decision inside
+    // its tags) into ring slot e; returns the decision.  The row is COPIED out of its slot into
+    // xs[] (RPC * EPT predicated moves) so that the body exists once, not once per slot: this kernel
+    // is latency-bound and its code used to be 150 KB -- the owner's path, run once per G rows by
+    // every CTA, was an instruction-cache miss from end to end (per-row time doubled with RPC).
+    auto decide = [&](int i, int sl, int iter, int e, bool project, const double (&qp)[EPT]) -> int {
         int d = GS_REMOVED;
+        unsigned long long *slot = ll + (int64_t)(e % nslot) * SLOT_WORDS;
+        double xs[EPT], ini = 0.0, old = 0.0;
+        int st = 2;
 #pragma unroll
         for (int s = 0; s < RPC; ++s) {
-            if (s != sl) continue;
-            if (state[s] == 2) continue;
+            if (s == sl) {
+#pragma unroll
+                for (int q = 0; q < EPT; ++q) xs[q] = x[s][q];
+                ini = init[s]; old = nrm[s]; st = state[s];
+            }
+        }
+        if (project && st == 0) {
+            double p1[1] = {0.0};
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) p1[0] = fma(qp[q], xs[q], p1[0]);
+            block_sum8<1>(p1, red);
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) xs[q] = fma(-p1[0], qp[q], xs[q]);
+            if (tid == 0) R[(int64_t)(i - 1) * r + i] = p1[0];      // first and only main-path term of R[i-1, i]
+        }
+        if (st != 2) {
             double ss[1] = {0.0};
 #pragma unroll
-            for (int q = 0; q < EPT; ++q) ss[0] = fma(x[s][q], x[s][q], ss[0]);
-            block_sum_n<1>(ss, red);
-            const double norm = sqrt(ss[0]), old = nrm[s];
-            nrm[s] = norm;
-            if (norm <= rtol * init[s]) d = GS_REMOVED;
+            for (int q = 0; q < EPT; ++q) ss[0] = fma(xs[q], xs[q], ss[0]);
+            block_sum8<1>(ss, red);
+            const double norm = sqrt(ss[0]);
+            if (norm <= rtol * ini) d = GS_REMOVED;
             else if (!(norm < thr * old) || iter >= GS_MAX_REITER) d = GS_FINAL;
             else d = GS_REITER;
+            old = norm;
             if (d == GS_FINAL) {
                 const double inv = 1.0 / norm;
 #pragma unroll
-                for (int q = 0; q < EPT; ++q) x[s][q] *= inv;
-                if (tid == 0) R[i * r + i] = norm;
-                state[s] = 1;
+                for (int q = 0; q < EPT; ++q) xs[q] *= inv;
+                if (tid == 0) R[(int64_t)i * r + i] = norm;
+                st = 1;
             }
             if (d == GS_REMOVED) {
                 if (tid == 0) flags[i] = 1;
-                state[s] = 2;
-            } else {
-#pragma unroll
-                for (int q = 0; q < EPT; ++q) {
-                    const int64_t c = tid + (int64_t)q * nthr;
-                    if (c < k) A[i * lda + c] = x[s][q];
-                }
+                st = 2;
             }
         }
-        __syncthreads();                               // CTA barrier + release store: cumulative, no fence needed
-        if (tid == 0) st_release_gpu_i32(ctrl + e, d);
+        const uint32_t tag = (uint32_t)((e + 1) << 2) | (uint32_t)d;
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int c = tid + q * nthr;
+            ll_store_f64(slot + 2 * c, xs[q], tag);                         // the hand-over: no fence, no flag
+            if (d == GS_FINAL && c < k) A[(int64_t)i * lda + c] = xs[q];    // the result (nobody reads it back)
+        }
+#pragma unroll
+        for (int s = 0; s < RPC; ++s) {
+            if (s == sl) {
+#pragma unroll
+                for (int q = 0; q < EPT; ++q) x[s][q] = xs[q];
+                nrm[s] = old; state[s] = st;
+            }
+        }
+        return d;
     };
 
-    int64_t ev = 0;
+    const int r32 = (int)r, off32 = (int)(offset < r ? offset : r);
+    int ev = 0;
     bool ahead = false;                                // decision of the current row already published (look-ahead)
-    for (int64_t i = 0; i < r; ++i) {
-        const int owner = (int)(i % G), slot = (int)(i / G);
+    int ahead_dec = 0;
+    int owner = 0, slot = 0;                           // i % G, i / G without a division per row
+    for (int i = 0; i < r32; ++i) {
         const bool mine = cta == owner;
         int iter = 0;
         while (true) {
-            int dec;
-            if (i < offset) {
-                dec = GS_FINAL;                        // given orthonormal row, untouched in global memory
-            } else {
-                if (mine && !ahead) decide(i, slot, iter, ev);
-                ahead = false;
-                dec = block_wait_ge(ctrl + ev, 1, timeout_ns, &s_slot);
-                if (dec < 0) {
-                    if (tid == 0) *status = 1;
-                    return;
+            int dec = GS_FINAL;
+            double q[EPT];
+            if (i < off32) {
+                // given orthonormal row, untouched in global memory
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int c = tid + e * nthr;
+                    q[e] = c < k ? ldcg_f64(A + (int64_t)i * lda + c) : 0.0;
                 }
+            } else if (mine) {
+                dec = ahead ? ahead_dec : decide(i, slot, iter, ev, false, q);
+                ahead = false;
+#pragma unroll
+                for (int s = 0; s < RPC; ++s) {
+                    if (s == slot) {
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) q[e] = x[s][e];       // the owner has the row in registers
+                    }
+                }
+                ++ev;
+            } else {
+                const unsigned long long *src = ll + (int64_t)(ev % nslot) * SLOT_WORDS + 2 * tid;
+                const uint32_t want = (uint32_t)(ev + 1);
+                const long long t0 = clock64(), limit = (long long)(2 * timeout_ns);
+                // ONE thread per CTA spins (G x 256 threads hammering the same lines of L2 slow every
+                // hand-over down, the owner's stores included); the others wait at the CTA barrier and
+                // then read -- and validate -- their own words
+                unsigned long long w0[EPT], w1[EPT];
+                if (poll_mode == 0) {
+                    if (tid == 0) {
+                        do {
+                            ll_ld(src, w0[0], w1[0]);
+                            if (clock64() - t0 > limit) { *status = 1; break; }
+                        } while (!ll_valid(w0[0], w1[0], want));
+                    }
+                    __syncthreads();
+                }
+                while (true) {
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) ll_ld(src + 2 * e * nthr, w0[e], w1[e]);
+                    bool ok = true;
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) ok &= ll_valid(w0[e], w1[e], want);
+                    if (ok) break;
+                    if (clock64() - t0 > limit) {
+                        *status = 1;
+                        return;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) q[e] = ll_value(w0[e], w1[e]);
+                dec = ll_decision(w0[0]);
                 ++ev;
             }
             if (dec == GS_REMOVED) break;
-            double q[EPT];
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int64_t c = tid + (int64_t)e * nthr;
-                q[e] = c < k ? ldcg_f64(A + i * lda + c) : 0.0;
-            }
             if (dec == GS_FINAL) {
-                // Look-ahead: the owner of row i+1 completes that row first and publishes its decision
-                // before it updates its other rows, so the chain q_i -> q_{i+1} never waits for
-                // trailing updates.
-                const int64_t i1 = i + 1;
+                // Look-ahead: the owner of row i+1 completes that row first and publishes it before it
+                // updates its other rows, so the chain q_i -> q_{i+1} never waits for trailing updates.
+                const int i1 = i + 1;
+                int o1 = owner + 1, sl1 = slot;
+                if (o1 == G) { o1 = 0; ++sl1; }
                 int skip = -1;
-                if (i1 < r && i1 >= offset && (int)(i1 % G) == cta) {
-                    const int sl1 = (int)(i1 / G);
-#pragma unroll
-                    for (int s = 0; s < RPC; ++s) {
-                        if (s != sl1 || state[s] != 0) continue;
-                        double p1[1] = {0.0};
-#pragma unroll
-                        for (int e = 0; e < EPT; ++e) p1[0] = fma(q[e], x[s][e], p1[0]);
-                        block_sum_n<1>(p1, red);
-#pragma unroll
-                        for (int e = 0; e < EPT; ++e) x[s][e] = fma(-p1[0], q[e], x[s][e]);
-                        if (tid == 0) R[i * r + i1] += p1[0];
-                    }
-                    decide(i1, sl1, 0, ev);
+                if (i1 < r32 && i1 >= off32 && o1 == cta) {
+                    ahead_dec = decide(i1, sl1, 0, ev, true, q);
                     ahead = true;
                     skip = sl1;
                 }
@@ -236,7 +369,7 @@ gs_grid_kernel(double *A, int64_t r, int64_t k, int64_t lda, int64_t offset, dou
                 bool any = false;
 #pragma unroll
                 for (int s = 0; s < RPC; ++s) {
-                    const int64_t l = (int64_t)s * G + cta;
+                    const int l = s * G + cta;
                     p[s] = 0.0;
                     if (l > i && state[s] == 0 && s != skip) {
                         any = true;
@@ -245,85 +378,152 @@ gs_grid_kernel(double *A, int64_t r, int64_t k, int64_t lda, int64_t offset, dou
                     }
                 }
                 if (any) {                             // uniform over the CTA
-                    block_sum_n<RPC>(p, red);
+                    block_sum8<RPC>(p, red);
 #pragma unroll
                     for (int s = 0; s < RPC; ++s) {
-                        const int64_t l = (int64_t)s * G + cta;
+                        const int l = s * G + cta;
                         if (l > i && state[s] == 0 && s != skip) {
 #pragma unroll
                             for (int e = 0; e < EPT; ++e) x[s][e] = fma(-p[s], q[e], x[s][e]);
-                            if (tid == 0) R[i * r + l] += p[s];
+                            if (tid == 0) R[(int64_t)i * r + l] = p[s];    // plain store: R[i, l] was 0 (no load on the path)
                         }
                     }
                 }
                 break;
             }
-            // dec == GS_REITER: re-iteration of row i (q holds its current, unnormalised content)
+            // dec == GS_REITER: re-iteration of row i (q holds its current, unnormalised content).  NOT
+            // rare: pyMOR re-iterates whenever a pass shrinks the row below 0.9 of its norm, i.e. for
+            // every row past i ~ 0.19 k of a random block (a third of the rows of BASELINE configs[4]).
+            // Every CTA computes the coefficients against the final rows it owns and its partial
+            // correction; partials travel with the fence-free tagged words of the row hand-over and are
+            // summed in TWO levels, in CTA order: group leaders (every NG-th CTA) add the partials of
+            // their NG members, the owner adds the leaders' sums -- two hand-over latencies and
+            // 2 * NG loads per thread instead of a fence + an atomic + G serial loads (22 -> 8 kcycles).
             {
-                const int64_t e_this = ev - 1;
+                const int e_this = ev - 1;
+                const uint32_t ptag = ((uint32_t)(e_this + 1) << 2) | (uint32_t)GS_REITER, pwant = (uint32_t)(e_this + 1);
+                const long long t0 = clock64(), limit = (long long)(2 * timeout_ns);
+                unsigned long long *part = ll + (int64_t)nslot * SLOT_WORDS;            // G partial slots
+                unsigned long long *lead = part + (int64_t)G * PART_WORDS;              // leader slots
                 double c_[RPC], v[EPT];
 #pragma unroll
                 for (int e = 0; e < EPT; ++e) v[e] = 0.0;
 #pragma unroll
                 for (int s = 0; s < RPC; ++s) {
-                    const int64_t j = (int64_t)s * G + cta;
+                    const int j = s * G + cta;
                     c_[s] = 0.0;
                     if (j < i && state[s] == 1) {
 #pragma unroll
                         for (int e = 0; e < EPT; ++e) c_[s] = fma(q[e], x[s][e], c_[s]);
                     }
                 }
-                block_sum_n<RPC>(c_, red);
+                block_sum8<RPC>(c_, red);
 #pragma unroll
                 for (int s = 0; s < RPC; ++s) {
-                    const int64_t j = (int64_t)s * G + cta;
-                    if (j < i) {
-                        if (state[s] == 1) {
+                    const int j = s * G + cta;
+                    const bool use = j < i && state[s] == 1;
+                    if (use) {
 #pragma unroll
-                            for (int e = 0; e < EPT; ++e) v[e] = fma(c_[s], x[s][e], v[e]);
-                        }
-                        if (tid == 0) coef[j] = state[s] == 1 ? c_[s] : 0.0;
+                        for (int e = 0; e < EPT; ++e) v[e] = fma(c_[s], x[s][e], v[e]);
                     }
+                    // coefficient of final row j = s G + cta, behind the partial vector of this CTA
+                    if (tid == 0) ll_store_f64(part + (int64_t)cta * PART_WORDS + SLOT_WORDS + 2 * s, use ? c_[s] : 0.0, ptag);
                 }
+                const int NG = G <= 4 ? G : (G <= 16 ? 4 : (G <= 64 ? 8 : 12));        // group size
+                const int my_lead = cta - cta % NG;
+                if (cta != my_lead) {
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const int64_t c = tid + (int64_t)e * nthr;
-                    if (c < k) scratch[(int64_t)cta * k + c] = v[e];
+                    for (int e = 0; e < EPT; ++e) ll_store_f64(part + (int64_t)cta * PART_WORDS + 2 * (tid + e * nthr), v[e], ptag);
+                } else {
+                    // leader: own partial first, then the members' in CTA order
+                    const int nmem = min(NG, G - cta) - 1;
+                    constexpr int U = EPT <= 4 ? 4 : (EPT <= 8 ? 2 : 1);
+                    for (int m0 = 0; m0 < nmem; m0 += U) {
+                        unsigned long long w0[U][EPT], w1[U][EPT];
+                        while (true) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int m = min(m0 + u, nmem - 1);          // a short last batch re-reads its last member
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e)
+                                    ll_ld(part + (int64_t)(cta + 1 + m) * PART_WORDS + 2 * (tid + e * nthr), w0[u][e], w1[u][e]);
+                            }
+                            bool ok = true;
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e) ok &= ll_valid(w0[u][e], w1[u][e], pwant);
+                            }
+                            if (ok) break;
+                            if (clock64() - t0 > limit) { *status = 1; return; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (m0 + u < nmem) {
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e) v[e] += ll_value(w0[u][e], w1[u][e]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) ll_store_f64(lead + (int64_t)(cta / NG) * SLOT_WORDS + 2 * (tid + e * nthr), v[e], ptag);
                 }
-                __threadfence();
-                __syncthreads();
-                if (tid == 0) red_release_gpu_add(done + e_this, 1);
                 if (mine) {
-                    if (block_wait_ge(done + e_this, G, timeout_ns, &s_slot) < 0) {
-                        if (tid == 0) *status = 1;
-                        return;
+                    const int nlead = (G + NG - 1) / NG;
+                    double tot[EPT];
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) tot[e] = 0.0;
+                    constexpr int U = EPT <= 4 ? 4 : (EPT <= 8 ? 2 : 1);
+                    for (int g0 = 0; g0 < nlead; g0 += U) {
+                        unsigned long long w0[U][EPT], w1[U][EPT];
+                        while (true) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int g = min(g0 + u, nlead - 1);
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e)
+                                    ll_ld(lead + (int64_t)g * SLOT_WORDS + 2 * (tid + e * nthr), w0[u][e], w1[u][e]);
+                            }
+                            bool ok = true;
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e) ok &= ll_valid(w0[u][e], w1[u][e], pwant);
+                            }
+                            if (ok) break;
+                            if (clock64() - t0 > limit) { *status = 1; return; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (g0 + u < nlead) {
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e) tot[e] += ll_value(w0[u][e], w1[u][e]);
+                            }
+                        }
                     }
 #pragma unroll
                     for (int s = 0; s < RPC; ++s) {
-                        if (s != slot) continue;
-                        constexpr int U = EPT <= 4 ? 8 : (EPT <= 8 ? 4 : 2);
-                        for (int g0 = 0; g0 < G; g0 += U) {           // U * EPT loads in flight, summed in CTA order
-                            double t[U][EPT];
+                        if (s == slot) {
 #pragma unroll
-                            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                                for (int e = 0; e < EPT; ++e) {
-                                    const int64_t c = tid + (int64_t)e * nthr;
-                                    t[u][e] = (g0 + u < G && c < k) ? ldcg_f64(scratch + (int64_t)(g0 + u) * k + c) : 0.0;
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                                for (int e = 0; e < EPT; ++e) x[s][e] -= t[u][e];
-                            }
+                            for (int e = 0; e < EPT; ++e) x[s][e] -= tot[e];
                         }
                     }
-                    for (int64_t j = tid; j < i; j += nthr) R[j * r + i] += ldcg_f64(coef + j);
+                    // coefficients of all final rows j < i: R[j, i] += c_j (c_j sits in slot (j % G), word (j / G))
+                    for (int j = tid; j < i; j += nthr) {
+                        const unsigned long long *src = part + (int64_t)(j % G) * PART_WORDS + SLOT_WORDS + 2 * (j / G);
+                        unsigned long long c0, c1;
+                        do {
+                            ll_ld(src, c0, c1);
+                            if (clock64() - t0 > limit) { *status = 1; return; }
+                        } while (!ll_valid(c0, c1, pwant));
+                        R[(int64_t)j * r + i] += ll_value(c0, c1);
+                    }
+                    __syncthreads();                   // the row is complete in every thread before it is judged again
                 }
                 ++iter;
             }
         }
+        if (++owner == G) { owner = 0; ++slot; }
     }
 }
 
@@ -633,7 +833,7 @@ static GsCfg gs_config(int64_t r, int64_t k) {
     int rpc = 0, e = 0;
     if (ept <= 4) { rpc = 8; e = 4; }
     else if (ept <= 8) { rpc = 8; e = 8; }
-    else if (ept <= 16) { rpc = 4; e = 16; }
+    else if (ept <= 16) { rpc = (r + 1) / 2 <= sms ? 2 : 4; e = 16; }   // 16 elements per thread: two rows per CTA keep the rows in registers
     else return c;
     // fewer rows per CTA = fewer dot products per step and CTA (the step is latency-bound), as long
     // as the grid stays co-resident; RLA_GS_RPC overrides (development)
@@ -655,16 +855,18 @@ using namespace rla;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct GsLayout { size_t scratch, coef, ctrl, done, status, total; };
+// ring slots of the row hand-over: nobody lags more than (GS_MAX_REITER + 1) (G + 1) events (see the kernel)
+static int gs_ll_slots(int G) { return (GS_MAX_REITER + 1) * (G + 2); }
+
+struct GsLayout { size_t status, ll, total; };
 static GsLayout gs_layout(const GsCfg &c, int64_t r, int64_t k) {
+    (void)r; (void)k;
     GsLayout L;
-    const size_t ev = (size_t)(GS_MAX_REITER + 1) * (size_t)r;
-    L.scratch = 0;
-    L.coef = align_up((size_t)c.grid * (size_t)k * sizeof(double), 16);
-    L.ctrl = align_up(L.coef + (size_t)r * sizeof(double), 16);
-    L.done = L.ctrl + ev * sizeof(int32_t);
-    L.status = L.done + ev * sizeof(int32_t);
-    L.total = align_up(L.status + sizeof(int32_t), 16);
+    const size_t slot_words = (size_t)2 * c.ept * 256, part_words = slot_words + (size_t)2 * c.rpc;
+    L.status = 0;
+    L.ll = 16;
+    L.total = L.ll + ((size_t)gs_ll_slots(c.grid) * slot_words + (size_t)c.grid * part_words + (size_t)c.grid * slot_words) *
+                         sizeof(unsigned long long);
     return L;
 }
 
@@ -694,19 +896,21 @@ extern "C" int rla_gram_schmidt_ws_f64(double *a, int64_t r, int64_t k, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
     const GsLayout L = gs_layout(c, r, k);
     char *base = static_cast<char *>(ws);
-    double *scratch = reinterpret_cast<double *>(base + L.scratch), *coef = reinterpret_cast<double *>(base + L.coef);
-    int32_t *ctrl = reinterpret_cast<int32_t *>(base + L.ctrl), *done = reinterpret_cast<int32_t *>(base + L.done);
     int32_t *status = reinterpret_cast<int32_t *>(base + L.status);
-    RLA_CUDA_CHECK(cudaMemsetAsync(ctrl, 0, L.total - L.ctrl, st));
+    unsigned long long *ll = reinterpret_cast<unsigned long long *>(base + L.ll);
+    int nslot = gs_ll_slots(c.grid);
+    // status and every tagged word start from zero (tag 0 matches no event)
+    RLA_CUDA_CHECK(cudaMemsetAsync(base, 0, L.total, st));
     unsigned long long timeout_ns = 5000000000ull;
-    void *args[] = {&a, &r, &k, &lda, &offset, &R, &flags, &atol, &rtol, &thr, &scratch, &coef, &ctrl, &done, &status,
-                    &timeout_ns};
+    int poll_mode = 0;
+    if (const char *env = getenv("RLA_GS_POLL")) poll_mode = atoi(env);      // development
+    void *args[] = {&a, &r, &k, &lda, &offset, &R, &flags, &atol, &rtol, &thr, &ll, &nslot, &status, &timeout_ns, &poll_mode};
     const void *fn = nullptr;
     if (c.ept == 4) fn = c.rpc == 8 ? (const void *)gs_grid_kernel<8, 4> : c.rpc == 4 ? (const void *)gs_grid_kernel<4, 4>
                                                                                     : (const void *)gs_grid_kernel<2, 4>;
     else if (c.ept == 8) fn = c.rpc == 8 ? (const void *)gs_grid_kernel<8, 8> : c.rpc == 4 ? (const void *)gs_grid_kernel<4, 8>
                                                                                          : (const void *)gs_grid_kernel<2, 8>;
-    else fn = (const void *)gs_grid_kernel<4, 16>;
+    else fn = c.rpc == 2 ? (const void *)gs_grid_kernel<2, 16> : (const void *)gs_grid_kernel<4, 16>;
     // cooperative launch: guarantees that all CTAs are co-resident (they wait on each other's flags)
     RLA_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(c.grid), dim3(256), args, 0, st));
     count_launch();
