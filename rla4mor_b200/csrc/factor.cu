@@ -5,16 +5,18 @@
 // the cost of the sequential synchronisation points, not flops or bytes.
 //
 //  * gs_grid_kernel: RIGHT-looking modified Gram-Schmidt.  Rows are dealt round-robin to G CTAs and
-//    live in registers.  Step i: the owner of row i normalises it and publishes q_i (one grid
-//    barrier); every CTA then projects q_i out of the rows it owns (all its dot products in one
-//    block reduction).  Row i has then received exactly the projections j = 0..i-1, in that order,
-//    that pyMOR's left-looking loop applies, so R, the removal test (norm <= rtol * initial) and the
-//    re-iteration test (norm < threshold * old norm) are pyMOR's.  A re-iteration pass (rare for
-//    well-conditioned blocks) is done by the whole grid at once: every CTA computes the
-//    coefficients against the final rows it owns and a partial correction, the owner sums the
-//    partials in CTA order.  (pyMOR re-iterates with sequential MGS; the second-pass coefficients
-//    are O(eps), so the two differ by O(eps^2).)  About one barrier per row instead of i block
-//    reductions per row: 256 x 1024 in about a millisecond instead of 18 ms.
+//    live in registers.  Step i: the owner of row i normalises it and hands q_i over; every CTA
+//    then projects q_i out of the rows it owns (all its dot products in one block reduction).  Row
+//    i has then received exactly the projections j = 0..i-1, in that order, that pyMOR's
+//    left-looking loop applies, so R, the removal test (norm <= rtol * initial) and the
+//    re-iteration test (norm < threshold * old norm) are pyMOR's.  A re-iteration pass is done by
+//    the whole grid at once: every CTA computes the coefficients against the final rows it owns
+//    and a partial correction, the partials are summed in two levels in CTA order.  (pyMOR
+//    re-iterates with sequential MGS; the second-pass coefficients are O(eps), so the two differ by
+//    O(eps^2).)  Round 2: rows, decisions, partial corrections and coefficients all travel as
+//    tagged 8-byte words ("LL" protocol: data and its own ready flag in one atomic word) -- no
+//    fence, no flag, no atomic on any path; a reader puts all its loads in flight before it checks
+//    any.  256 x 1024: 18 ms (one CTA) -> 1.6 ms (round 1) -> 1.0 ms.
 //
 //  * jacobi_block_kernel: rows are grouped in blocks of B; a CTA holds a PAIR of blocks (2B rows of
 //    the sketch and of the accumulated rotations) in shared memory and rotates all B*B cross pairs
@@ -183,7 +185,7 @@ template <int RPC, int EPT>
 __global__ void __launch_bounds__(256, 1)
 gs_grid_kernel(double *A, int64_t r, int64_t k, int64_t lda, int64_t offset, double *R,
                int32_t *flags, double atol, double rtol, double thr,
-               unsigned long long *ll, int nslot, int32_t *status, unsigned long long timeout_ns, int poll_mode) {
+               unsigned long long *ll, int nslot, int32_t *status, unsigned long long timeout_ns) {
     // (no __restrict__: other CTAs write these buffers while the kernel runs)
     __shared__ __align__(16) double red[RPC][8];
     const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
@@ -321,19 +323,17 @@ gs_grid_kernel(double *A, int64_t r, int64_t k, int64_t lda, int64_t offset, dou
                 const unsigned long long *src = ll + (int64_t)(ev % nslot) * SLOT_WORDS + 2 * tid;
                 const uint32_t want = (uint32_t)(ev + 1);
                 const long long t0 = clock64(), limit = (long long)(2 * timeout_ns);
-                // ONE thread per CTA spins (G x 256 threads hammering the same lines of L2 slow every
-                // hand-over down, the owner's stores included); the others wait at the CTA barrier and
-                // then read -- and validate -- their own words
+                // ONE thread per CTA spins; the others wait at the CTA barrier and then read -- and
+                // validate -- their own words (G x 256 spinning threads on the same lines of L2 measured
+                // 3-5 % slower, with or without a __nanosleep back-off)
                 unsigned long long w0[EPT], w1[EPT];
-                if (poll_mode == 0) {
-                    if (tid == 0) {
-                        do {
-                            ll_ld(src, w0[0], w1[0]);
-                            if (clock64() - t0 > limit) { *status = 1; break; }
-                        } while (!ll_valid(w0[0], w1[0], want));
-                    }
-                    __syncthreads();
+                if (tid == 0) {
+                    do {
+                        ll_ld(src, w0[0], w1[0]);
+                        if (clock64() - t0 > limit) { *status = 1; break; }
+                    } while (!ll_valid(w0[0], w1[0], want));
                 }
+                __syncthreads();
                 while (true) {
 #pragma unroll
                     for (int e = 0; e < EPT; ++e) ll_ld(src + 2 * e * nthr, w0[e], w1[e]);
@@ -902,9 +902,7 @@ extern "C" int rla_gram_schmidt_ws_f64(double *a, int64_t r, int64_t k, int64_t 
     // status and every tagged word start from zero (tag 0 matches no event)
     RLA_CUDA_CHECK(cudaMemsetAsync(base, 0, L.total, st));
     unsigned long long timeout_ns = 5000000000ull;
-    int poll_mode = 0;
-    if (const char *env = getenv("RLA_GS_POLL")) poll_mode = atoi(env);      // development
-    void *args[] = {&a, &r, &k, &lda, &offset, &R, &flags, &atol, &rtol, &thr, &ll, &nslot, &status, &timeout_ns, &poll_mode};
+    void *args[] = {&a, &r, &k, &lda, &offset, &R, &flags, &atol, &rtol, &thr, &ll, &nslot, &status, &timeout_ns};
     const void *fn = nullptr;
     if (c.ept == 4) fn = c.rpc == 8 ? (const void *)gs_grid_kernel<8, 4> : c.rpc == 4 ? (const void *)gs_grid_kernel<4, 4>
                                                                                     : (const void *)gs_grid_kernel<2, 4>;
