@@ -222,11 +222,13 @@ int rla_svd_jacobi_f64(double *a_dev, int64_t k, int64_t m, int64_t lda,
                        double *s_dev, double *V_dev, const int32_t *pairs_dev, int32_t *rot_dev,
                        int max_sweeps, double tol, int *sweeps_done, void *stream);
 
-/* Grid-synchronised (cooperative-launch) versions of the two factorisations (csrc/factor.cu).
- * rla_gram_schmidt_ws_f64: same contract as rla_gram_schmidt_f64, rows dealt to many CTAs with
- * one grid barrier per row (right-looking modified Gram-Schmidt, pyMOR's removal / re-iteration
- * tests); falls back to the one-CTA kernel when the shape is out of range or ws is too small
- * (rla_gram_schmidt_workspace_bytes returns 0 when the grid kernel does not apply). */
+/* Many-CTA (cooperative-launch) versions of the two factorisations (csrc/factor.cu).
+ * rla_gram_schmidt_ws_f64: same contract as rla_gram_schmidt_f64, rows dealt to many CTAs and kept
+ * in registers (right-looking modified Gram-Schmidt, pyMOR's removal / re-iteration tests); a
+ * finished row, its decision and the partial corrections of a re-iteration travel between CTAs as
+ * tagged 8-byte words in the workspace (no fence, no flag); falls back to the one-CTA kernel when
+ * the shape is out of range or ws is too small (rla_gram_schmidt_workspace_bytes returns 0 when
+ * the many-CTA kernel does not apply; the workspace holds the hand-over ring, a few MB). */
 size_t rla_gram_schmidt_workspace_bytes(int64_t r, int64_t k);
 /* Byte offset, inside the workspace, of the int32 status word the grid kernel leaves behind
  * (0 = ok, 1 = a wait on another CTA's flag timed out: the result is NOT usable); -1 when the
