@@ -81,8 +81,13 @@ def gram_schmidt(A, offset=0, atol=1e-13, rtol=1e-13, reiteration_threshold=9e-1
               "rla_gram_schmidt_ws_f64")
         soff = lib().rla_gram_schmidt_status_offset(r, k)
     keep = flags[:r] == 0
-    all_kept = bool(keep.all())                     # synchronises: the status word below is final
-    if soff >= 0 and soff + 4 <= ws.numel() and int(ws[soff:soff + 4].view(torch.int32).item()) != 0:
+    have_status = soff >= 0 and soff + 4 <= ws.numel()
+    # ONE device-to-host read for both answers (number of removed rows, status word of the kernel)
+    removed = (flags[:r] != 0).sum().to(torch.int32).view(1)
+    word = ws[soff:soff + 4].view(torch.int32) if have_status else torch.zeros_like(removed)
+    n_removed, status = torch.cat([removed, word]).tolist()
+    all_kept = n_removed == 0
+    if have_status and status != 0:
         # a CTA gave up waiting for another CTA's flag (pre-emption, debugger, shared GPU):
         # Q and R are only partly orthogonalised
         raise RlaError("gram_schmidt: the grid-synchronised kernel timed out waiting on a flag; result discarded")
@@ -183,8 +188,9 @@ def svd_jacobi(S, want_v=False, max_sweeps=30, tol=None, block=True, cluster=Tru
                   "rla_svd_jacobi_f64")
     order = torch.argsort(s, descending=True)
     if B or C:
-        svd_jacobi.last_phases = scratch[3:8].tolist() if C else None   # kilo-cycles per phase (cluster kernel)
-        info = scratch[:3].cpu()                    # {sweeps, converged, timeout}; the sort above follows the launch anyway
+        host = scratch[:8].cpu() if C else scratch[:3].cpu()    # one read: {sweeps, converged, timeout}[, phase kilo-cycles]
+        svd_jacobi.last_phases = host[3:8].tolist() if C else None
+        info = host[:3]
         if int(info[2]) != 0:
             raise RlaError("svd_jacobi: the block kernel timed out waiting on a block flag; result discarded")
         svd_jacobi.last_info = info
