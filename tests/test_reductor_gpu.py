@@ -312,3 +312,24 @@ def test_sketched_reductor_at_fem_size(rb):
     u_full = a @ red.rb
     true_res = sum(t * op.apply(space.from_numpy(u_full.reshape(1, -1))).data[0] for t, op in zip(th, ops_dev)) - f[0]
     assert 0.8 < err / float(torch.linalg.norm(true_res)) < 1.2           # k = 1000 embedding of one vector
+
+
+def test_thin_qr_dgks_threshold(rb):
+    """The range finder's QR re-iterates by the Daniel-Gragg-Kaufman-Stewart rule (1/sqrt(2)) instead
+    of pyMOR's 0.9: orthogonality stays at rounding level on random, graded and nearly dependent rows,
+    and the factors agree with the 0.9 rule's."""
+    from rla4mor_b200.rangefinder import thin_qr
+    rs = np.random.RandomState(21)
+    blocks = [rs.standard_normal((256, 1024)),
+              rs.standard_normal((96, 96)) @ (np.logspace(0, -8, 96)[:, None] * rs.standard_normal((96, 400)))]
+    near = rs.standard_normal((64, 300))
+    near[40] = near[3] + 1e-7 * near[40]                                  # forces a second pass under either rule
+    blocks.append(near)
+    for A in blocks:
+        Q, R = thin_qr(_dev(A))
+        Q9, R9 = thin_qr(_dev(A), reiteration_threshold=0.9)
+        r = Q.shape[0]
+        assert Q.shape == Q9.shape and r == A.shape[0]
+        assert rel_fro((Q @ Q.T).cpu().numpy(), np.eye(r)) < 1e-12
+        assert rel_fro((R.T @ Q).cpu().numpy(), A) < 1e-13
+        assert rel_fro(R.cpu().numpy(), R9.cpu().numpy()) < 1e-9
