@@ -125,7 +125,10 @@ class SketchedReductor:
         # triangular solve over Q m right-hand sides walks the factor once instead of Q times
         # (n = 10^6, Q = 4, m = 64: 37 ms instead of 4 x 13 ms; its short root levels are latency-bound)
         rows = [b.shape[0] for b in blocks]
-        if self.inverse_product is not None and len(blocks) > 1 and sum(rows) * self.space.dim * 8 <= self.batch_bytes:
+        # (the concatenated block, the solver's transposed copy and the result live at the same time:
+        # keep the block under a quarter of the free memory)
+        limit = min(self.batch_bytes, torch.cuda.mem_get_info()[0] // 4)
+        if self.inverse_product is not None and len(blocks) > 1 and sum(rows) * self.space.dim * 8 <= limit:
             solved = list(torch.split(self._rinv(torch.cat(blocks, dim=0)), rows, dim=0))
         else:
             solved = [self._rinv(b) for b in blocks]

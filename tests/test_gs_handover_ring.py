@@ -57,3 +57,37 @@ def test_publisher_never_laps_the_slowest_consumer(G):
         # uniformly random schedules, and schedules in which one CTA almost never runs
         assert worst_lag(G, 4 * G + 3, seed) < nslot
         assert worst_lag(G, 4 * G + 3, seed, slow=seed % G) < nslot
+
+
+def _warp_reduce_multi(vals):
+    """Python replay of warp_reduce_multi<N> (csrc/factor.cu): vals[lane][n]; returns v[0] per lane."""
+    N = len(vals[0])
+    lg = N.bit_length() - 1
+    v = [list(x) for x in vals]
+    for s in range(lg):
+        M, o = N >> s, 16 >> s
+        new = [list(x) for x in v]
+        for lane in range(32):
+            upper = (lane & o) != 0
+            for j in range(M // 2):
+                send_partner = v[lane ^ o][j] if (((lane ^ o) & o) != 0) else v[lane ^ o][j + M // 2]
+                keep = v[lane][j + M // 2] if upper else v[lane][j]
+                new[lane][j] = keep + send_partner
+        v = new
+    o = 16 >> lg
+    while o:
+        v = [[v[lane][0] + v[lane ^ o][0]] + v[lane][1:] for lane in range(32)]
+        o >>= 1
+    return [x[0] for x in v]
+
+
+@pytest.mark.parametrize("N", [1, 2, 4, 8, 16])
+def test_multi_value_warp_reduction_lands_sum_n_on_lane_group_n(N):
+    """After the exchange levels lane l holds the warp sum of the ORIGINAL value l >> (5 - log2 N):
+    the layout block_sum8 relies on when it writes the warp partials."""
+    rnd = random.Random(N)
+    vals = [[rnd.randint(-1000, 1000) for _ in range(N)] for _ in range(32)]
+    out = _warp_reduce_multi(vals)
+    sh = 5 - (N.bit_length() - 1)
+    for lane in range(32):
+        assert out[lane] == sum(vals[l][lane >> sh] for l in range(32))
