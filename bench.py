@@ -18,7 +18,9 @@ A step is one pass of the hot path over one block of synthetic vectors.  Workloa
                         full on the CPU: the oracle's whole srht() is timed beside it, L2 flushed
                         between steps because the 105 MB block fits the 126 MB L2); `secondary`
     sketched_reductor_c4  SketchedReductor.extend_basis on an n = 1e6, Q = 4 FEM-like problem with the
-                        LU inverse product (configs[3]; tools/bench_c4.py); `secondary`, rank 0
+                        LU inverse product (configs[3]; tools/bench_c4.py; the inverse product of all Q
+                        terms is ONE sparse triangular solve of Q m right-hand sides, whose HBM
+                        roofline the line carries); `secondary`, rank 0
     rangefinder_c5      sketch + thin QR / SVD of a 2^23 x 256 block, k=1024, ROW-sharded with one
                         exchange of the (m, k) partials over NVLink peer memory (configs[4]);
                         second `secondary` result (tools/bench_c5.py)
