@@ -333,3 +333,17 @@ def test_thin_qr_dgks_threshold(rb):
         assert rel_fro((Q @ Q.T).cpu().numpy(), np.eye(r)) < 1e-12
         assert rel_fro((R.T @ Q).cpu().numpy(), A) < 1e-13
         assert rel_fro(R.cpu().numpy(), R9.cpu().numpy()) < 1e-9
+
+
+@pytest.mark.parametrize("r,k", [(300, 700), (200, 512), (90, 256)])
+def test_gram_schmidt_many_reiterations_ragged_groups(rb, r, k):
+    """Random rows filling a large part of the space: pyMOR's rule re-iterates every row past
+    i ~ 0.19 k, and the number of CTAs (75, 50, 45) is not a multiple of the leader-group size of the
+    two-level sum of the partial corrections.  R and Q against the oracle's sequential loop."""
+    from rla4mor_b200 import reductor_ops as ops
+    A = np.random.RandomState(r * 7 + k).standard_normal((r, k))
+    Qd, Rd = ops.gram_schmidt(_dev(A))
+    Qo, Ro = ro.gram_schmidt(A)
+    assert Qd.shape == Qo.shape == (r, k)
+    assert rel_fro(Rd.cpu().numpy(), Ro) < 1e-12 and rel_fro(Qd.cpu().numpy(), Qo) < 1e-10
+    assert rel_fro((Qd @ Qd.T).cpu().numpy(), np.eye(r)) < 1e-13
